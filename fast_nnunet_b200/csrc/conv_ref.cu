@@ -1,0 +1,328 @@
+// CUDA-core direct convolution / transposed convolution, residual join and average pooling.
+//
+// This is the general-shape back end of the per-patch network forward (any channel count, kernel
+// 1|3 per axis, stride 1|2 per axis).  It is used for the layers the tcgen05 implicit-GEMM kernel
+// (conv_umma.cu) does not cover (e.g. the first layer with 1 or 4 input channels) and as the on-device
+// cross-check of that kernel.  Semantics follow torch.nn.Conv3d / ConvTranspose3d / InstanceNorm3d /
+// LeakyReLU as composed by dynamic_network_architectures' ConvDropoutNormReLU, StackedConvBlocks,
+// BasicBlockD and UNetDecoder (call site: predict_from_raw_data.py:543 `self.network(x)`).
+//
+// Fusion contract shared with conv_umma.cu:
+//   * the source is read RAW (pre-norm) and the producing layer's InstanceNorm affine + LeakyReLU is
+//     applied while loading (per (sample, channel) scale/shift from the fp64 sums);
+//   * the output is written RAW (conv + bias, rounded to fp16) and the per-(sample, channel) sum and
+//     sum of squares of the ROUNDED values are accumulated in fp64 for the consumer.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace fnnu {
+
+constexpr int kVX = 4;    // output voxels per thread (consecutive along the innermost axis)
+constexpr int kCO = 16;   // output channels per thread
+constexpr int kCI = 8;    // input channels per smem weight chunk
+constexpr int kThreads = 128;
+
+__global__ void __launch_bounds__(kThreads) conv_direct_kernel(ConvArgs a) {
+  extern __shared__ float smem[];
+  const int ntaps_blk = a.transposed ? 1 : a.ntaps;
+  float* w_s = smem;                                   // [ntaps_blk][kCI][kCO]
+  float* xs = w_s + ntaps_blk * kCI * kCO;             // scale [cin]
+  float* xh = xs + a.cin;                              // shift [cin]
+  float* xl = xh + a.cin;                              // slope [cin]
+  float* red = xl + a.cin;                             // [kThreads/32][2*kCO]
+
+  const int b = blockIdx.z;
+  const int n_co_chunks = a.cout_pad / kCO;
+  const int co_chunk = blockIdx.y % n_co_chunks;
+  const int tap_fixed = blockIdx.y / n_co_chunks;      // transposed only
+  const int co0 = co_chunk * kCO;
+
+  // Domain the threads iterate over: conv -> output voxels; transposed -> input voxels.
+  const int D0 = a.transposed ? a.in_d[0] : a.out_d[0];
+  const int D1 = a.transposed ? a.in_d[1] : a.out_d[1];
+  const int D2 = a.transposed ? a.in_d[2] : a.out_d[2];
+  const int groups_per_row = (D2 + kVX - 1) / kVX;
+  const long long n_groups = (long long)D0 * D1 * groups_per_row;
+  const long long gidx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool active = gidx < n_groups;
+  int x0 = 0, y = 0, z = 0;
+  if (active) {
+    x0 = (int)(gidx % groups_per_row) * kVX;
+    y = (int)((gidx / groups_per_row) % D1);
+    z = (int)(gidx / ((long long)groups_per_row * D1));
+  }
+
+  // pending transform of the source channels for this sample
+  for (int c = threadIdx.x; c < a.cin; c += kThreads) {
+    float sc, sh;
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, a.src_meta[c], a.src_inv_count, sc, sh);
+    xs[c] = sc;
+    xh[c] = sh;
+    xl[c] = a.src_meta[c].eps < 0.f ? 1.f : a.src_meta[c].slope;
+  }
+
+  float acc[kVX][kCO];
+#pragma unroll
+  for (int v = 0; v < kVX; ++v)
+#pragma unroll
+    for (int o = 0; o < kCO; ++o) acc[v][o] = 0.f;
+
+  const size_t in_row = (size_t)a.src_cs;
+  const __half* src_b = a.src + (size_t)b * a.in_d[0] * a.in_d[1] * a.in_d[2] * in_row;
+  const bool vec_in = (a.src_cs % 8 == 0) && (((uintptr_t)a.src) % 16 == 0);
+
+  for (int ci0 = 0; ci0 < a.cin; ci0 += kCI) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntaps_blk * kCI * kCO; i += kThreads) {
+      int o = i % kCO;
+      int c = (i / kCO) % kCI;
+      int t = i / (kCO * kCI);
+      int tap = a.transposed ? tap_fixed : t;
+      int ci = ci0 + c;
+      w_s[i] = (ci < a.cin) ? __ldg(a.w + ((size_t)tap * a.cin + ci) * a.cout_pad + co0 + o) : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int t = 0; t < ntaps_blk; ++t) {
+      int iz, iy, ixb, xstep;
+      if (a.transposed) {
+        iz = z; iy = y; ixb = x0; xstep = 1;
+      } else {
+        int kx = t % a.k[2];
+        int ky = (t / a.k[2]) % a.k[1];
+        int kz = t / (a.k[2] * a.k[1]);
+        iz = z * a.s[0] + kz - a.pad[0];
+        iy = y * a.s[1] + ky - a.pad[1];
+        ixb = x0 * a.s[2] + kx - a.pad[2];
+        xstep = a.s[2];
+        if (iz < 0 || iz >= a.in_d[0] || iy < 0 || iy >= a.in_d[1]) continue;
+      }
+      float in[kVX][kCI];
+#pragma unroll
+      for (int v = 0; v < kVX; ++v) {
+        int ix = ixb + v * xstep;
+        bool ok = ix >= 0 && ix < a.in_d[2] && (x0 + v) < D2;
+        const __half* p = src_b + (((size_t)iz * a.in_d[1] + iy) * a.in_d[2] + (ok ? ix : 0)) * in_row + ci0;
+        if (ok && vec_in && ci0 + kCI <= a.cin) {
+          uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int c = 0; c < kCI; c += 2) {
+            float2 f = __half22float2(h2[c >> 1]);
+            in[v][c] = lrelu(fmaf(f.x, xs[ci0 + c], xh[ci0 + c]), xl[ci0 + c]);
+            in[v][c + 1] = lrelu(fmaf(f.y, xs[ci0 + c + 1], xh[ci0 + c + 1]), xl[ci0 + c + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCI; ++c) {
+            float val = 0.f;
+            if (ok && ci0 + c < a.cin) {
+              float f = __half2float(p[c]);
+              val = lrelu(fmaf(f, xs[ci0 + c], xh[ci0 + c]), xl[ci0 + c]);
+            }
+            in[v][c] = val;
+          }
+        }
+      }
+      const float4* wt = reinterpret_cast<const float4*>(w_s + (size_t)t * kCI * kCO);
+#pragma unroll
+      for (int c = 0; c < kCI; ++c) {
+        float4 w0 = wt[c * 4 + 0], w1 = wt[c * 4 + 1], w2 = wt[c * 4 + 2], w3 = wt[c * 4 + 3];
+        float wv[kCO] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                         w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int v = 0; v < kVX; ++v)
+#pragma unroll
+          for (int o = 0; o < kCO; ++o) acc[v][o] = fmaf(in[v][c], wv[o], acc[v][o]);
+      }
+    }
+  }
+
+  // epilogue: bias, round to fp16, store, InstanceNorm sums of the rounded values
+  float s1[kCO], s2[kCO];
+#pragma unroll
+  for (int o = 0; o < kCO; ++o) s1[o] = s2[o] = 0.f;
+  if (active) {
+    int oz, oy, oxb, oxstep;
+    if (a.transposed) {
+      int dx = tap_fixed % a.s[2];
+      int dy = (tap_fixed / a.s[2]) % a.s[1];
+      int dz = tap_fixed / (a.s[2] * a.s[1]);
+      oz = z * a.s[0] + dz; oy = y * a.s[1] + dy; oxb = x0 * a.s[2] + dx; oxstep = a.s[2];
+    } else {
+      oz = z; oy = y; oxb = x0; oxstep = 1;
+    }
+    __half* dst_b = a.dst + (size_t)b * a.out_d[0] * a.out_d[1] * a.out_d[2] * a.dst_cs;
+    const bool vec_out = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && (co0 + kCO <= a.cout);
+#pragma unroll
+    for (int v = 0; v < kVX; ++v) {
+      if (x0 + v >= D2) continue;
+      int ox = oxb + v * oxstep;
+      __half* q = dst_b + (((size_t)oz * a.out_d[1] + oy) * a.out_d[2] + ox) * a.dst_cs + co0;
+      __half hv[kCO];
+#pragma unroll
+      for (int o = 0; o < kCO; ++o) {
+        float val = acc[v][o] + ((a.bias && co0 + o < a.cout) ? __ldg(a.bias + co0 + o) : 0.f);
+        hv[o] = __float2half_rn(val);
+        float r = __half2float(hv[o]);
+        s1[o] += r;
+        s2[o] += r * r;
+      }
+      if (vec_out) {
+        reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
+        reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < kCO; ++o)
+          if (co0 + o < a.cout) q[o] = hv[o];
+      }
+    }
+  }
+  if (a.dst_stats) {
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < kCO; ++o) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        s1[o] += __shfl_xor_sync(0xffffffffu, s1[o], off);
+        s2[o] += __shfl_xor_sync(0xffffffffu, s2[o], off);
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < kCO; ++o) {
+        red[warp * 2 * kCO + o] = s1[o];
+        red[warp * 2 * kCO + kCO + o] = s2[o];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kCO) {
+      int o = threadIdx.x % kCO;
+      int which = threadIdx.x / kCO;
+      double tot = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) tot += (double)red[w * 2 * kCO + which * kCO + o];
+      if (co0 + o < a.cout) atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + co0 + o) * 2 + which, tot);
+    }
+  }
+}
+
+int launch_conv_direct(const ConvArgs& a, cudaStream_t s) {
+  const int D0 = a.transposed ? a.in_d[0] : a.out_d[0];
+  const int D1 = a.transposed ? a.in_d[1] : a.out_d[1];
+  const int D2 = a.transposed ? a.in_d[2] : a.out_d[2];
+  long long groups = (long long)D0 * D1 * ((D2 + kVX - 1) / kVX);
+  dim3 grid((unsigned)((groups + kThreads - 1) / kThreads),
+            (unsigned)((a.cout_pad / kCO) * (a.transposed ? a.ntaps : 1)), (unsigned)a.batch);
+  int ntaps_blk = a.transposed ? 1 : a.ntaps;
+  size_t smem = (size_t)(ntaps_blk * kCI * kCO + 3 * a.cin + (kThreads / 32) * 2 * kCO) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv_direct: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return FNNU_E_CUDA;
+    }
+  }
+  conv_direct_kernel<<<grid, kThreads, smem, s>>>(a);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: PyTorch layouts -> [tap][cin][cout_pad] fp32
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_direct_kernel(const float* __restrict__ w, float* __restrict__ out, int cin, int cout,
+                                           int cout_pad, int ntaps, int transposed) {
+  size_t total = (size_t)ntaps * cin * cout_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % cout_pad);
+    int ci = (int)((i / cout_pad) % cin);
+    int tap = (int)(i / ((size_t)cout_pad * cin));
+    float v = 0.f;
+    if (co < cout) {
+      size_t src = transposed ? (((size_t)ci * cout + co) * ntaps + tap) : (((size_t)co * cin + ci) * ntaps + tap);
+      v = w[src];
+    }
+    out[i] = v;
+  }
+}
+
+int launch_pack_weights_direct(const float* w_dev, float* out, int cin, int cout, int cout_pad, int ntaps,
+                               int transposed, cudaStream_t s) {
+  size_t total = (size_t)ntaps * cin * cout_pad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_direct_kernel<<<blocks, 256, 0, s>>>(w_dev, out, cin, cout, cout_pad, ntaps, transposed);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual join: dst = lrelu_slope(xform(a) + xform(b)), stored ready to use
+// average pooling: dst = mean over the stride window of xform(src), stored ready to use
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_act_kernel(EltArgs a) {
+  const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
+  const size_t total = nv * a.c * a.batch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % a.c);
+    size_t v = (i / a.c) % nv;
+    int b = (int)(i / ((size_t)a.c * nv));
+    float sc, sh, sc2, sh2;
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, a.src_meta[c], a.inv_count, sc, sh);
+    xform_from_stats(a.src2_stats + ((size_t)b * a.src2_stat_stride + c) * 2, a.src2_meta[c], a.inv_count, sc2, sh2);
+    float sl1 = a.src_meta[c].eps < 0.f ? 1.f : a.src_meta[c].slope;
+    float sl2 = a.src2_meta[c].eps < 0.f ? 1.f : a.src2_meta[c].slope;
+    float x1 = lrelu(fmaf(__half2float(a.src[((size_t)b * nv + v) * a.src_cs + c]), sc, sh), sl1);
+    float x2 = lrelu(fmaf(__half2float(a.src2[((size_t)b * nv + v) * a.src2_cs + c]), sc2, sh2), sl2);
+    a.dst[((size_t)b * nv + v) * a.dst_cs + c] = __float2half_rn(lrelu(x1 + x2, a.slope));
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_kernel(EltArgs a) {
+  // a.d = OUTPUT dims; input dims = a.d * a.s
+  const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
+  const size_t total = nv * a.c * a.batch;
+  const int I1 = a.d[1] * a.s[1], I2 = a.d[2] * a.s[2];
+  const size_t nvi = nv * a.s[0] * a.s[1] * a.s[2];
+  const float inv = 1.f / (float)(a.s[0] * a.s[1] * a.s[2]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % a.c);
+    size_t v = (i / a.c) % nv;
+    int b = (int)(i / ((size_t)a.c * nv));
+    int x = (int)(v % a.d[2]);
+    int y = (int)((v / a.d[2]) % a.d[1]);
+    int z = (int)(v / ((size_t)a.d[2] * a.d[1]));
+    float sc, sh;
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, a.src_meta[c], a.inv_count, sc, sh);
+    float sl = a.src_meta[c].eps < 0.f ? 1.f : a.src_meta[c].slope;
+    float sum = 0.f;
+    for (int dz = 0; dz < a.s[0]; ++dz)
+      for (int dy = 0; dy < a.s[1]; ++dy)
+        for (int dx = 0; dx < a.s[2]; ++dx) {
+          size_t iv = ((size_t)(z * a.s[0] + dz) * I1 + (y * a.s[1] + dy)) * I2 + (x * a.s[2] + dx);
+          sum += lrelu(fmaf(__half2float(a.src[((size_t)b * nvi + iv) * a.src_cs + c]), sc, sh), sl);
+        }
+    a.dst[((size_t)b * nv + v) * a.dst_cs + c] = __float2half_rn(sum * inv);
+  }
+}
+
+int launch_add_act(const EltArgs& a, cudaStream_t s) {
+  size_t total = (size_t)a.d[0] * a.d[1] * a.d[2] * a.c * a.batch;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_act_kernel<<<blocks, 256, 0, s>>>(a);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+int launch_avgpool(const EltArgs& a, cudaStream_t s) {
+  size_t total = (size_t)a.d[0] * a.d[1] * a.d[2] * a.c * a.batch;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  avgpool_kernel<<<blocks, 256, 0, s>>>(a);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+}  // namespace fnnu

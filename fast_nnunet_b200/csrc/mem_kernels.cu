@@ -1,0 +1,442 @@
+// Memory-bound operators of the sliding window: tile gather (+mirror), TTA-mean + Gaussian weight +
+// accumulate, weight-sum map, normalise + inf check + argmax, halo add.
+// Reference semantics: distillation/nnunetv2/inference/predict_from_raw_data.py:541-631.
+// All kernels are HBM-bound; they use 128-bit accesses where the innermost start is 16-byte aligned
+// and grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace fnnu {
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather: volume fp32 [C][X][Y][Z] -> tiles fp16 [n_tiles*n_flips][pX][pY][pZ][cs]
+// ------------------------------------------------------------------------------------------------
+struct FlipList {
+  uint8_t m[8];
+};
+
+__global__ void __launch_bounds__(256) gather_tiles_kernel(
+    const float* __restrict__ vol, int C, int X, int Y, int Z, const int32_t* __restrict__ starts,
+    int n_tiles, int pX, int pY, int pZ, FlipList flips, int n_flips, __half* __restrict__ out, int cs) {
+  const size_t pvox = (size_t)pX * pY * pZ;
+  const size_t total = pvox * n_tiles * n_flips;
+  const size_t vstride = (size_t)X * Y * Z;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t n = i / pvox;
+    size_t r = i - n * pvox;
+    int z = (int)(r % pZ);
+    int y = (int)((r / pZ) % pY);
+    int x = (int)(r / ((size_t)pZ * pY));
+    int t = (int)(n / n_flips);
+    int f = flips.m[n - (size_t)t * n_flips];
+    int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
+    int gx = sx + ((f & 1) ? pX - 1 - x : x);
+    int gy = sy + ((f & 2) ? pY - 1 - y : y);
+    int gz = sz + ((f & 4) ? pZ - 1 - z : z);
+    const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
+    __half* dst = out + i * cs;
+    for (int c = 0; c < C; ++c) dst[c] = __float2half_rn(__ldg(src + c * vstride));
+    for (int c = C; c < cs; ++c) dst[c] = __float2half_rn(0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulate: one launch per tile (tiles of a batch overlap, so they are applied in order).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename AccT>
+__device__ __forceinline__ void acc_add(AccT* p, float v);
+template <>
+__device__ __forceinline__ void acc_add<float>(float* p, float v) { *p = __fadd_rn(*p, v); }
+template <>
+__device__ __forceinline__ void acc_add<__half>(__half* p, float v) {
+  *p = __float2half_rn(__fadd_rn(__half2float(*p), v));
+}
+
+// Generic path: any heads / stride / alignment.  One thread per tile voxel.
+template <typename InT, typename AccT>
+__global__ void __launch_bounds__(256) accumulate_generic_kernel(
+    const InT* __restrict__ preds, int ps, int heads, int sx, int sy, int sz, int pX, int pY, int pZ,
+    FlipList flips, int n_flips, const __half* __restrict__ gauss, AccT* __restrict__ acc, int X, int Y,
+    int Z) {
+  const size_t pvox = (size_t)pX * pY * pZ;
+  const size_t hstride = (size_t)X * Y * Z;
+  const float inv_dummy = (float)n_flips;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pvox;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int z = (int)(i % pZ);
+    int y = (int)((i / pZ) % pY);
+    int x = (int)(i / ((size_t)pZ * pY));
+    float g = gauss ? __half2float(gauss[i]) : 1.f;
+    size_t a = ((size_t)(sx + x) * Y + (sy + y)) * Z + (sz + z);
+    for (int h = 0; h < heads; ++h) {
+      float s = 0.f;
+      for (int f = 0; f < n_flips; ++f) {
+        int m = flips.m[f];
+        int fx = (m & 1) ? pX - 1 - x : x;
+        int fy = (m & 2) ? pY - 1 - y : y;
+        int fz = (m & 4) ? pZ - 1 - z : z;
+        size_t src = ((size_t)f * pvox + ((size_t)fx * pY + fy) * pZ + fz) * ps + h;
+        float v = to_f<InT>(preds[src]);
+        s = (f == 0) ? v : __fadd_rn(s, v);
+      }
+      if (n_flips > 1) s = __fdiv_rn(s, inv_dummy);
+      if (gauss) s = __fmul_rn(s, g);
+      acc_add<AccT>(acc + h * hstride + a, s);
+    }
+  }
+}
+
+// Fast path: fp16 predictions, 2 heads stored as half2 per voxel, fp32 accumulators, pZ % 4 == 0,
+// (sz % 4 == 0 && Z % 4 == 0): one thread handles 4 consecutive z voxels with 128-bit accesses.
+__global__ void __launch_bounds__(256) accumulate_h2_vec4_kernel(
+    const __half* __restrict__ preds, int sx, int sy, int sz, int pX, int pY, int pZ, FlipList flips,
+    int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
+  const int zq = pZ >> 2;
+  const size_t nthreads = (size_t)pX * pY * zq;
+  const size_t pvox = (size_t)pX * pY * pZ;
+  const size_t hstride = (size_t)X * Y * Z;
+  const float nf = (float)n_flips;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int z = (int)(i % zq) << 2;
+    int y = (int)((i / zq) % pY);
+    int x = (int)(i / ((size_t)zq * pY));
+    float s0[4], s1[4];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      if (f < n_flips) {
+        int m = flips.m[f];
+        int fx = (m & 1) ? pX - 1 - x : x;
+        int fy = (m & 2) ? pY - 1 - y : y;
+        bool rz = (m & 4) != 0;
+        int fz = rz ? pZ - 4 - z : z;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
+            preds + ((size_t)f * pvox + ((size_t)fx * pY + fy) * pZ + fz) * 2));
+        const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 v = __half22float2(hp[rz ? 3 - k : k]);
+          if (f == 0) {
+            s0[k] = v.x;
+            s1[k] = v.y;
+          } else {
+            s0[k] = __fadd_rn(s0[k], v.x);
+            s1[k] = __fadd_rn(s1[k], v.y);
+          }
+        }
+      }
+    }
+    float g[4] = {1.f, 1.f, 1.f, 1.f};
+    if (gauss) {
+      const uint2 graw = __ldg(reinterpret_cast<const uint2*>(gauss + ((size_t)x * pY + y) * pZ + z));
+      const __half2* gp = reinterpret_cast<const __half2*>(&graw);
+      float2 g01 = __half22float2(gp[0]), g23 = __half22float2(gp[1]);
+      g[0] = g01.x; g[1] = g01.y; g[2] = g23.x; g[3] = g23.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (n_flips > 1) {
+        s0[k] = __fdiv_rn(s0[k], nf);
+        s1[k] = __fdiv_rn(s1[k], nf);
+      }
+      if (gauss) {
+        s0[k] = __fmul_rn(s0[k], g[k]);
+        s1[k] = __fmul_rn(s1[k], g[k]);
+      }
+    }
+    size_t a = ((size_t)(sx + x) * Y + (sy + y)) * Z + (sz + z);
+    float4* a0 = reinterpret_cast<float4*>(acc + a);
+    float4* a1 = reinterpret_cast<float4*>(acc + hstride + a);
+    float4 v0 = *a0, v1 = *a1;
+    v0.x = __fadd_rn(v0.x, s0[0]); v0.y = __fadd_rn(v0.y, s0[1]);
+    v0.z = __fadd_rn(v0.z, s0[2]); v0.w = __fadd_rn(v0.w, s0[3]);
+    v1.x = __fadd_rn(v1.x, s1[0]); v1.y = __fadd_rn(v1.y, s1[1]);
+    v1.z = __fadd_rn(v1.z, s1[2]); v1.w = __fadd_rn(v1.w, s1[3]);
+    *a0 = v0;
+    *a1 = v1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight sum (n_predictions): gather over the covering tiles, in tile order.
+// ------------------------------------------------------------------------------------------------
+#define FNNU_MAX_STEPS 160
+struct StepLists {
+  int32_t s[3][FNNU_MAX_STEPS];
+  int n[3];
+};
+
+template <typename AccT>
+__global__ void __launch_bounds__(256) weight_sum_kernel(StepLists st, int pX, int pY, int pZ,
+                                                         const __half* __restrict__ gauss,
+                                                         AccT* __restrict__ wsum, int X, int Y, int Z) {
+  const size_t total = (size_t)X * Y * Z;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int z = (int)(i % Z);
+    int y = (int)((i / Z) % Y);
+    int x = (int)(i / ((size_t)Z * Y));
+    float w = 0.f;
+    for (int a = 0; a < st.n[0]; ++a) {
+      int lx = x - st.s[0][a];
+      if (lx < 0 || lx >= pX) continue;
+      for (int b = 0; b < st.n[1]; ++b) {
+        int ly = y - st.s[1][b];
+        if (ly < 0 || ly >= pY) continue;
+        for (int c = 0; c < st.n[2]; ++c) {
+          int lz = z - st.s[2][c];
+          if (lz < 0 || lz >= pZ) continue;
+          float g = gauss ? __half2float(__ldg(gauss + ((size_t)lx * pY + ly) * pZ + lz)) : 1.f;
+          w = __fadd_rn(w, g);
+          if (sizeof(AccT) == 2) w = __half2float(__float2half_rn(w));
+        }
+      }
+    }
+    if (sizeof(AccT) == 2)
+      reinterpret_cast<__half*>(wsum)[i] = __float2half_rn(w);
+    else
+      reinterpret_cast<float*>(wsum)[i] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: logits = acc / wsum (rounded to fp16 like the reference's half buffers), inf check,
+// argmax with first-maximum tie-break.
+// ------------------------------------------------------------------------------------------------
+template <typename AccT>
+__global__ void __launch_bounds__(256) finalize_kernel(const AccT* __restrict__ acc,
+                                                       const AccT* __restrict__ wsum, int heads,
+                                                       size_t nvox, __half* __restrict__ logits,
+                                                       uint8_t* __restrict__ labels,
+                                                       int32_t* __restrict__ inf_flag) {
+  bool saw_inf = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float w = to_f<AccT>(wsum[i]);
+    float best = 0.f;
+    int arg = 0;
+    for (int h = 0; h < heads; ++h) {
+      float v = __fdiv_rn(to_f<AccT>(acc[(size_t)h * nvox + i]), w);
+      __half hv = __float2half_rn(v);
+      float r = __half2float(hv);
+      if (isinf(r)) saw_inf = true;
+      if (logits) logits[(size_t)h * nvox + i] = hv;
+      if (h == 0 || r > best) {   // strict '>' keeps the first maximum (numpy argmax)
+        best = r;
+        arg = h;
+      }
+    }
+    if (labels) labels[i] = (uint8_t)arg;
+  }
+  if (saw_inf && inf_flag) atomicOr(inf_flag, 1);
+}
+
+// 2 heads, fp32 accumulators, nvox % 4 == 0: 128-bit loads, 64-bit logit stores, 32-bit label stores.
+__global__ void __launch_bounds__(256) finalize_h2_vec4_kernel(const float* __restrict__ acc,
+                                                               const float* __restrict__ wsum,
+                                                               size_t nvox, __half* __restrict__ logits,
+                                                               uint8_t* __restrict__ labels,
+                                                               int32_t* __restrict__ inf_flag) {
+  bool saw_inf = false;
+  const size_t nq = nvox >> 2;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
+       q += (size_t)gridDim.x * blockDim.x) {
+    float4 w = __ldg(reinterpret_cast<const float4*>(wsum) + q);
+    float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + q);
+    float4 a1 = __ldg(reinterpret_cast<const float4*>(acc + nvox) + q);
+    float wv[4] = {w.x, w.y, w.z, w.w};
+    float v0[4] = {a0.x, a0.y, a0.z, a0.w};
+    float v1[4] = {a1.x, a1.y, a1.z, a1.w};
+    __half h0[4], h1[4];
+    uint32_t lab = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h0[k] = __float2half_rn(__fdiv_rn(v0[k], wv[k]));
+      h1[k] = __float2half_rn(__fdiv_rn(v1[k], wv[k]));
+      float r0 = __half2float(h0[k]), r1 = __half2float(h1[k]);
+      if (isinf(r0) || isinf(r1)) saw_inf = true;
+      if (r1 > r0) lab |= (1u << (8 * k));
+    }
+    if (logits) {
+      uint2 o0, o1;
+      o0.x = (uint32_t)__half_as_ushort(h0[0]) | ((uint32_t)__half_as_ushort(h0[1]) << 16);
+      o0.y = (uint32_t)__half_as_ushort(h0[2]) | ((uint32_t)__half_as_ushort(h0[3]) << 16);
+      o1.x = (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16);
+      o1.y = (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16);
+      reinterpret_cast<uint2*>(logits)[q] = o0;
+      reinterpret_cast<uint2*>(logits + nvox)[q] = o1;
+    }
+    if (labels) reinterpret_cast<uint32_t*>(labels)[q] = lab;
+  }
+  if (saw_inf && inf_flag) atomicOr(inf_flag, 1);
+}
+
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ acc,
+                                                          const float* __restrict__ other, size_t n) {
+  const size_t nq = n >> 2;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
+       q += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(acc)[q];
+    float4 b = __ldg(reinterpret_cast<const float4*>(other) + q);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(acc)[q] = a;
+  }
+  for (size_t i = (nq << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    acc[i] += other[i];
+}
+
+static inline int grid_for(size_t work_items, int threads, int waves_cap = 16) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * waves_cap;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace fnnu
+
+using namespace fnnu;
+
+extern "C" int fnnu_gather_tiles(const float* volume, int channels, const int vol_dims[3],
+                                 const int32_t* starts_dev, int n_tiles, const int patch[3],
+                                 const uint8_t* flip_masks, int n_flips, void* out, int c_stride,
+                                 void* stream) {
+  FNNU_CHECK_ARG(volume && starts_dev && out && vol_dims && patch && flip_masks, "gather: null pointer");
+  FNNU_CHECK_ARG(n_tiles > 0 && n_flips >= 1 && n_flips <= 8, "gather: n_tiles=%d n_flips=%d", n_tiles, n_flips);
+  FNNU_CHECK_ARG(channels >= 1 && c_stride >= channels, "gather: channels=%d stride=%d", channels, c_stride);
+  for (int a = 0; a < 3; ++a)
+    FNNU_CHECK_ARG(patch[a] >= 1 && vol_dims[a] >= patch[a], "gather: volume smaller than patch on axis %d", a);
+  FlipList fl;
+  for (int i = 0; i < 8; ++i) fl.m[i] = i < n_flips ? (flip_masks[i] & 7) : 0;
+  size_t total = (size_t)patch[0] * patch[1] * patch[2] * n_tiles * n_flips;
+  gather_tiles_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      volume, channels, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1],
+      patch[2], fl, n_flips, (__half*)out, c_stride);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stride, int heads,
+                                     const int32_t* starts_host, int n_tiles, const int patch[3],
+                                     const uint8_t* flip_masks, int n_flips, const void* gaussian,
+                                     void* acc, int acc_dtype, const int vol_dims[3], void* stream) {
+  FNNU_CHECK_ARG(preds && starts_host && acc && vol_dims && patch && flip_masks, "accumulate: null pointer");
+  FNNU_CHECK_ARG(n_tiles > 0 && n_flips >= 1 && n_flips <= 8, "accumulate: n_tiles=%d n_flips=%d", n_tiles, n_flips);
+  FNNU_CHECK_ARG(heads >= 1 && p_stride >= heads, "accumulate: heads=%d stride=%d", heads, p_stride);
+  FNNU_CHECK_ARG(in_dtype == FNNU_IN_F16 || in_dtype == FNNU_IN_F32, "accumulate: in_dtype=%d", in_dtype);
+  FNNU_CHECK_ARG(acc_dtype == FNNU_ACC_F32 || acc_dtype == FNNU_ACC_F16, "accumulate: acc_dtype=%d", acc_dtype);
+  FlipList fl;
+  for (int i = 0; i < 8; ++i) fl.m[i] = i < n_flips ? (flip_masks[i] & 7) : 0;
+  const int pX = patch[0], pY = patch[1], pZ = patch[2];
+  const int X = vol_dims[0], Y = vol_dims[1], Z = vol_dims[2];
+  const size_t pvox = (size_t)pX * pY * pZ;
+  const size_t esz = in_dtype == FNNU_IN_F16 ? 2 : 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int t = 0; t < n_tiles; ++t) {
+    int sx = starts_host[t * 3 + 0], sy = starts_host[t * 3 + 1], sz = starts_host[t * 3 + 2];
+    FNNU_CHECK_ARG(sx >= 0 && sy >= 0 && sz >= 0 && sx + pX <= X && sy + pY <= Y && sz + pZ <= Z,
+                   "accumulate: tile %d (%d,%d,%d) outside the volume", t, sx, sy, sz);
+    const char* p = (const char*)preds + (size_t)t * n_flips * pvox * p_stride * esz;
+    bool vec = in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32 && heads == 2 && p_stride == 2 &&
+               (pZ % 4 == 0) && (sz % 4 == 0) && (Z % 4 == 0) && (((uintptr_t)p) % 16 == 0) &&
+               (((uintptr_t)acc) % 16 == 0) && (!gaussian || ((uintptr_t)gaussian) % 8 == 0);
+    if (vec) {
+      accumulate_h2_vec4_kernel<<<grid_for(pvox / 4, 256), 256, 0, s>>>(
+          (const __half*)p, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian, (float*)acc, X, Y, Z);
+    } else if (in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32) {
+      accumulate_generic_kernel<__half, float><<<grid_for(pvox, 256), 256, 0, s>>>(
+          (const __half*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
+          (float*)acc, X, Y, Z);
+    } else if (in_dtype == FNNU_IN_F16) {
+      accumulate_generic_kernel<__half, __half><<<grid_for(pvox, 256), 256, 0, s>>>(
+          (const __half*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
+          (__half*)acc, X, Y, Z);
+    } else if (acc_dtype == FNNU_ACC_F32) {
+      accumulate_generic_kernel<float, float><<<grid_for(pvox, 256), 256, 0, s>>>(
+          (const float*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
+          (float*)acc, X, Y, Z);
+    } else {
+      accumulate_generic_kernel<float, __half><<<grid_for(pvox, 256), 256, 0, s>>>(
+          (const float*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
+          (__half*)acc, X, Y, Z);
+    }
+    FNNU_LAUNCH_CHECK();
+  }
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_weight_sum(const int32_t* steps_x, int nx, const int32_t* steps_y, int ny,
+                               const int32_t* steps_z, int nz, const int patch[3], const void* gaussian,
+                               void* wsum, int acc_dtype, const int vol_dims[3], void* stream) {
+  FNNU_CHECK_ARG(steps_x && steps_y && steps_z && patch && wsum && vol_dims, "weight_sum: null pointer");
+  FNNU_CHECK_ARG(nx >= 1 && ny >= 1 && nz >= 1 && nx <= FNNU_MAX_STEPS && ny <= FNNU_MAX_STEPS && nz <= FNNU_MAX_STEPS,
+                 "weight_sum: step counts %d %d %d (max %d per axis)", nx, ny, nz, FNNU_MAX_STEPS);
+  FNNU_CHECK_ARG(acc_dtype == FNNU_ACC_F32 || acc_dtype == FNNU_ACC_F16, "weight_sum: acc_dtype=%d", acc_dtype);
+  StepLists st;
+  st.n[0] = nx; st.n[1] = ny; st.n[2] = nz;
+  for (int i = 0; i < nx; ++i) st.s[0][i] = steps_x[i];
+  for (int i = 0; i < ny; ++i) st.s[1][i] = steps_y[i];
+  for (int i = 0; i < nz; ++i) st.s[2][i] = steps_z[i];
+  size_t total = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (acc_dtype == FNNU_ACC_F32)
+    weight_sum_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(st, patch[0], patch[1], patch[2],
+        (const __half*)gaussian, (float*)wsum, vol_dims[0], vol_dims[1], vol_dims[2]);
+  else
+    weight_sum_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(st, patch[0], patch[1], patch[2],
+        (const __half*)gaussian, (__half*)wsum, vol_dims[0], vol_dims[1], vol_dims[2]);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, int heads,
+                             const int vol_dims[3], void* logits_out, uint8_t* labels_out,
+                             int32_t* inf_flag_dev, void* stream) {
+  FNNU_CHECK_ARG(acc && wsum && vol_dims, "finalize: null pointer");
+  FNNU_CHECK_ARG(heads >= 1 && heads <= 255, "finalize: heads=%d", heads);
+  FNNU_CHECK_ARG(acc_dtype == FNNU_ACC_F32 || acc_dtype == FNNU_ACC_F16, "finalize: acc_dtype=%d", acc_dtype);
+  size_t nvox = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = acc_dtype == FNNU_ACC_F32 && heads == 2 && nvox % 4 == 0 && ((uintptr_t)acc % 16 == 0) &&
+             ((uintptr_t)wsum % 16 == 0) && (!logits_out || (uintptr_t)logits_out % 8 == 0) &&
+             (!labels_out || (uintptr_t)labels_out % 4 == 0);
+  if (vec)
+    finalize_h2_vec4_kernel<<<grid_for(nvox / 4, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, nvox,
+                                                                    (__half*)logits_out, labels_out, inf_flag_dev);
+  else if (acc_dtype == FNNU_ACC_F32)
+    finalize_kernel<float><<<grid_for(nvox, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, heads, nvox,
+                                                               (__half*)logits_out, labels_out, inf_flag_dev);
+  else
+    finalize_kernel<__half><<<grid_for(nvox, 256), 256, 0, s>>>((const __half*)acc, (const __half*)wsum, heads, nvox,
+                                                                (__half*)logits_out, labels_out, inf_flag_dev);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream) {
+  FNNU_CHECK_ARG(acc && other, "add_inplace: null pointer");
+  FNNU_CHECK_ARG(((uintptr_t)acc % 16 == 0) && ((uintptr_t)other % 16 == 0), "add_inplace: pointers must be 16-byte aligned");
+  if (n == 0) return FNNU_OK;
+  add_inplace_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(acc, other, n);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}

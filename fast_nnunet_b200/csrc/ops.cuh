@@ -1,0 +1,65 @@
+// Internal launch interfaces shared by engine.cu, conv_ref.cu and conv_umma.cu.
+#pragma once
+#include "common.cuh"
+
+namespace fnnu {
+
+struct ConvArgs {
+  const __half* src;        // first input channel of sample 0
+  int src_cs;
+  const double* src_stats;  // sums of the source channels (offset to the first input channel)
+  const ChanMeta* src_meta;
+  int src_stat_stride;
+  double src_inv_count;
+  __half* dst;              // first output channel of sample 0
+  int dst_cs;
+  double* dst_stats;        // or nullptr (no InstanceNorm after this op)
+  int dst_stat_stride;
+  const float* w;           // direct kernel: [tap][cin][cout_pad] fp32
+  const void* w_umma;       // tcgen05 kernel: packed fp16 blob (see conv_umma.cu) or nullptr
+  const float* bias;        // [cout] or nullptr
+  int cin, cout, cout_pad;
+  int in_d[3], out_d[3];
+  int k[3], s[3], pad[3];
+  int ntaps;
+  int transposed;
+  int batch;
+};
+
+struct EltArgs {
+  const __half* src;
+  int src_cs;
+  const double* src_stats;
+  const ChanMeta* src_meta;
+  int src_stat_stride;
+  const __half* src2;
+  int src2_cs;
+  const double* src2_stats;
+  const ChanMeta* src2_meta;
+  int src2_stat_stride;
+  __half* dst;
+  int dst_cs;
+  int d[3];     // output dims
+  int s[3];     // pooling stride (avgpool)
+  int c;
+  int batch;
+  double inv_count;   // 1 / voxels of the SOURCE buffer(s)
+  float slope;
+};
+
+int num_sms();
+
+int launch_conv_direct(const ConvArgs& a, cudaStream_t s);
+int launch_pack_weights_direct(const float* w_dev, float* out, int cin, int cout, int cout_pad, int ntaps,
+                               int transposed, cudaStream_t s);
+int launch_add_act(const EltArgs& a, cudaStream_t s);
+int launch_avgpool(const EltArgs& a, cudaStream_t s);
+
+// tcgen05 implicit-GEMM back end (conv_umma.cu)
+bool umma_supported(const ConvArgs& a);
+size_t umma_packed_weight_bytes(int cin, int cout, int ntaps, int transposed);
+int launch_pack_weights_umma(const float* w_dev, void* out, int cin, int cout, const int k[3], int transposed,
+                             cudaStream_t s);
+int launch_conv_umma(const ConvArgs& a, cudaStream_t s);
+
+}  // namespace fnnu

@@ -1,0 +1,417 @@
+"""nnUNetPredictor — drop-in for the reference's sliding-window inference path
+(distillation/nnunetv2/inference/predict_from_raw_data.py:39-680) running on libfnnu (sm_100a).
+
+Same constructor keywords, method names, argument meaning and error behaviour as the reference class
+for: __init__ (:40-65), initialize_from_trained_model_folder (:67-129), manual_initialization
+(:131-154), predict_sliding_window_return_logits (:634-680), predict_logits_from_preprocessed_data
+(:471-504), predict_single_npy_array (:423-468).  What differs is underneath:
+
+  * the volume stays resident on the device; tiles (and their mirrored copies) are cut by a gather
+    kernel instead of a Python producer thread + queue (:568-582);
+  * `self.network(x)` and the 8-pass mirror loop (:541-557) become ONE batched engine forward over
+    tiles x flips;
+  * `prediction *= gaussian; predicted_logits[sl] += prediction` (:611-613) is one fused kernel with fp32
+    accumulators (fp16 accumulators, the reference's arithmetic, on request);
+  * `n_predictions` (:614) is produced by one pass (it does not depend on the image);
+  * there is no CPU fallback (:663-672): errors surface as exceptions.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, engine as E
+from . import sliding_window as sw
+from .model_folder import effective_arch
+from .plans import ConfigurationManager, PlansManager, determine_num_input_channels, load_json
+from .program import Program, build_program, clean_state_dict
+
+
+def _infer_arch_from_weights(cls_name: str, kw: dict, sd: dict) -> dict:
+    """Makes features / conv / block counts agree with the checkpoint itself (so a distilled student is
+    loaded correctly even when the plans describe the teacher and init_args are incomplete)."""
+    kw = dict(kw)
+    sd = clean_state_dict(sd)
+    n = int(kw['n_stages'])
+    resenc = cls_name.endswith('ResidualEncoderUNet')
+    feats = []
+    for s in range(n):
+        key = f'encoder.stages.{s}.blocks.0.conv1.conv.weight' if resenc else f'encoder.stages.{s}.0.convs.0.conv.weight'
+        if key not in sd:
+            raise KeyError(f'checkpoint is missing parameter {key!r}')
+        feats.append(int(sd[key].shape[0]))
+    kw['features_per_stage'] = feats
+    if resenc:
+        kw['n_blocks_per_stage'] = [
+            len({k.split('.')[4] for k in sd if k.startswith(f'encoder.stages.{s}.blocks.')}) for s in range(n)]
+    else:
+        kw['n_conv_per_stage'] = [
+            len({k.split('.')[5] for k in sd if k.startswith(f'encoder.stages.{s}.0.convs.')}) for s in range(n)]
+    kw['n_conv_per_stage_decoder'] = [
+        len({k.split('.')[4] for k in sd if k.startswith(f'decoder.stages.{l}.convs.')}) for l in range(n - 1)]
+    kw['conv_bias'] = (('encoder.stem.convs.0.conv.bias' if resenc else 'encoder.stages.0.0.convs.0.conv.bias') in sd)
+    return kw
+
+
+class CompiledNetwork:
+    """Stands where the reference keeps `self.network` (an nn.Module).  `load_state_dict` lowers the
+    weights into a libfnnu engine; calling it runs a batch of channels-first patches (tests)."""
+
+    def __init__(self, network_class_name: str, arch_kwargs: dict, in_channels: int, num_heads: int,
+                 patch_size: Sequence[int]):
+        self.network_class_name = network_class_name
+        self.arch_kwargs = arch_kwargs
+        self.in_channels = in_channels
+        self.num_heads = num_heads
+        self.patch_size = tuple(int(p) for p in patch_size)
+        self.device = None
+        self.max_batch = None
+        self._engines = {}
+        self._current = None
+        self.program: Optional[Program] = None
+
+    # nn.Module-looking no-ops so that reference-style calling code keeps working
+    def to(self, device):
+        self.device = torch.device(device)
+        return self
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, params: dict, strict: bool = True):
+        self._current = params
+        return self
+
+    def engine(self, device: torch.device, max_batch: int) -> E.NetworkEngine:
+        if self._current is None:
+            raise RuntimeError('no parameters loaded (call load_state_dict / initialize_* first)')
+        key = (id(self._current), str(device), int(max_batch))
+        if key not in self._engines:
+            kw = _infer_arch_from_weights(self.network_class_name, self.arch_kwargs, self._current)
+            prog = build_program(self.network_class_name, self._current, kw, self.in_channels, self.num_heads,
+                                 self.patch_size)
+            self._engines = {k: v for k, v in self._engines.items() if k[0] == key[0]}   # one fold resident
+            self._engines[key] = E.NetworkEngine(prog, max_batch, device)
+            self.program = prog
+        return self._engines[key]
+
+    @torch.inference_mode()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (n, c, *patch) on the CUDA device -> logits (n, heads, *patch) fp16."""
+        assert x.ndim == 5 and tuple(x.shape[2:]) == self.patch_size and x.shape[1] == self.in_channels
+        eng = self.engine(x.device, max(int(x.shape[0]), 1))
+        n = x.shape[0]
+        inp = eng.buffer_tensor(eng.program.input_buffer, n)
+        inp.copy_(x.permute(0, 2, 3, 4, 1))
+        eng.forward(n)
+        out = eng.buffer_tensor(eng.program.output_buffer, n)
+        return out.permute(0, 4, 1, 2, 3).contiguous()
+
+
+class nnUNetPredictor(object):
+    def __init__(self,
+                 tile_step_size: float = 0.5,
+                 use_gaussian: bool = True,
+                 use_mirroring: bool = True,
+                 perform_everything_on_device: bool = True,
+                 device: torch.device = torch.device('cuda'),
+                 verbose: bool = False,
+                 verbose_preprocessing: bool = False,
+                 allow_tqdm: bool = True,
+                 *,
+                 tiles_per_batch: Optional[int] = None,
+                 accumulator_dtype: torch.dtype = torch.float32):
+        self.verbose = verbose
+        self.verbose_preprocessing = verbose_preprocessing
+        self.allow_tqdm = allow_tqdm
+
+        self.plans_manager, self.configuration_manager, self.list_of_parameters, self.network, self.dataset_json, \
+            self.trainer_name, self.allowed_mirroring_axes, self.label_manager = (None,) * 8
+
+        self.tile_step_size = tile_step_size
+        self.use_gaussian = use_gaussian
+        self.use_mirroring = use_mirroring
+        device = torch.device(device)
+        if device.type != 'cuda':
+            print('perform_everything_on_device=True is only supported for cuda devices! Setting this to False')
+            perform_everything_on_device = False
+        self.device = device
+        self.perform_everything_on_device = perform_everything_on_device
+        assert accumulator_dtype in (torch.float32, torch.float16)
+        self.accumulator_dtype = accumulator_dtype
+        self.tiles_per_batch = tiles_per_batch
+        self.last_launches = 0          # kernels launched by the last predict_* call (bench evidence)
+        self._gauss_cache = {}
+
+    # ------------------------------------------------------------------ model loading
+    def initialize_from_trained_model_folder(self, model_training_output_dir: str,
+                                             use_folds: Union[Tuple[Union[int, str]], None],
+                                             checkpoint_name: str = 'checkpoint_final.pth'):
+        """This is used when making predictions with a trained model."""
+        if use_folds is None:
+            use_folds = nnUNetPredictor.auto_detect_available_folds(model_training_output_dir, checkpoint_name)
+
+        dataset_json = load_json(os.path.join(model_training_output_dir, 'dataset.json'))
+        plans = load_json(os.path.join(model_training_output_dir, 'plans.json'))
+        plans_manager = PlansManager(plans)
+
+        if isinstance(use_folds, (str, int)):
+            use_folds = [use_folds]
+
+        parameters = []
+        trainer_name = configuration_name = inference_allowed_mirroring_axes = init_args = None
+        for i, f in enumerate(use_folds):
+            f = int(f) if f != 'all' else f
+            checkpoint = torch.load(os.path.join(model_training_output_dir, f'fold_{f}', checkpoint_name),
+                                    map_location=torch.device('cpu'), weights_only=False)
+            if i == 0:
+                trainer_name = checkpoint['trainer_name']
+                init_args = checkpoint['init_args']
+                configuration_name = init_args['configuration']
+                inference_allowed_mirroring_axes = checkpoint['inference_allowed_mirroring_axes'] if \
+                    'inference_allowed_mirroring_axes' in checkpoint.keys() else None
+            parameters.append(checkpoint['network_weights'])
+
+        configuration_manager = plans_manager.get_configuration(configuration_name)
+        num_input_channels = determine_num_input_channels(plans_manager, configuration_manager, dataset_json)
+        label_manager = plans_manager.get_label_manager(dataset_json)
+        cls, kw = effective_arch(configuration_manager.network_arch_class_name,
+                                 configuration_manager.network_arch_init_kwargs, trainer_name, init_args,
+                                 plans_manager.plans.get('plans_name', ''))
+        network = CompiledNetwork(cls, kw, num_input_channels, label_manager.num_segmentation_heads,
+                                  configuration_manager.patch_size)
+
+        self.plans_manager = plans_manager
+        self.configuration_manager = configuration_manager
+        self.list_of_parameters = parameters
+        network.load_state_dict(parameters[0])
+        self.network = network
+        self.dataset_json = dataset_json
+        self.trainer_name = trainer_name
+        self.allowed_mirroring_axes = inference_allowed_mirroring_axes
+        self.label_manager = label_manager
+
+    def manual_initialization(self, network, plans_manager: PlansManager,
+                              configuration_manager: ConfigurationManager, parameters: Optional[List[dict]],
+                              dataset_json: dict, trainer_name: str,
+                              inference_allowed_mirroring_axes: Optional[Tuple[int, ...]]):
+        """This is used by the nnUNetTrainer to initialize nnUNetPredictor for the final validation.
+        `network` may be a live torch.nn.Module (its state_dict is lowered) or a CompiledNetwork."""
+        self.plans_manager = plans_manager
+        self.configuration_manager = configuration_manager
+        self.dataset_json = dataset_json
+        self.trainer_name = trainer_name
+        self.allowed_mirroring_axes = inference_allowed_mirroring_axes
+        self.label_manager = plans_manager.get_label_manager(dataset_json)
+        if not isinstance(network, CompiledNetwork):
+            sd = network.state_dict()
+            num_input_channels = determine_num_input_channels(plans_manager, configuration_manager, dataset_json)
+            mod = getattr(network, 'module', network)
+            mod = getattr(mod, '_orig_mod', mod)
+            cname = type(getattr(mod, 'network', mod)).__name__
+            cls = configuration_manager.network_arch_class_name
+            if cname in ('LiteResEncStudent', 'ResidualEncoderUNet'):
+                cls = 'dynamic_network_architectures.architectures.unet.ResidualEncoderUNet'
+            elif cname in ('LiteNNUNetStudent', 'PlainConvUNet'):
+                cls = 'dynamic_network_architectures.architectures.unet.PlainConvUNet'
+            compiled = CompiledNetwork(cls, configuration_manager.network_arch_init_kwargs, num_input_channels,
+                                       self.label_manager.num_segmentation_heads, configuration_manager.patch_size)
+            if parameters is None:
+                parameters = [sd]
+            compiled.load_state_dict(parameters[0])
+            network = compiled
+        self.list_of_parameters = parameters
+        self.network = network
+
+    @staticmethod
+    def auto_detect_available_folds(model_training_output_dir, checkpoint_name):
+        print('use_folds is None, attempting to auto detect available folds')
+        fold_folders = [i for i in sorted(os.listdir(model_training_output_dir))
+                        if i.startswith('fold_') and os.path.isdir(os.path.join(model_training_output_dir, i))]
+        fold_folders = [i for i in fold_folders if i != 'fold_all']
+        fold_folders = [i for i in fold_folders
+                        if os.path.isfile(os.path.join(model_training_output_dir, i, checkpoint_name))]
+        use_folds = [int(i.split('_')[-1]) for i in fold_folders]
+        print(f'found the following folds: {use_folds}')
+        return use_folds
+
+    # ------------------------------------------------------------------ geometry helpers
+    def _flip_masks(self) -> bytes:
+        """Mirror combinations in the reference's order (:550-553): identity first, then every non-empty
+        subset of the allowed axes ordered by size then lexicographically.  bit a = flip spatial axis a."""
+        mirror_axes = self.allowed_mirroring_axes if self.use_mirroring else None
+        masks = [0]
+        if mirror_axes is not None:
+            assert max(mirror_axes) <= 2, 'mirror_axes does not match the dimension of the input!'
+            axes = list(mirror_axes)
+            for i in range(len(axes)):
+                for c in itertools.combinations(axes, i + 1):
+                    masks.append(sum(1 << int(a) for a in c))
+        return bytes(masks)
+
+    def _internal_get_sliding_window_slicers(self, image_size: Tuple[int, ...]):
+        """Same return value as the reference method (:506-538) for 3-D patches."""
+        patch = self.configuration_manager.patch_size
+        assert len(patch) == len(image_size) == 3, 'only 3-D patch sizes are supported by the B200 engine'
+        starts = sw.tile_starts(image_size, patch, self.tile_step_size)
+        return [tuple([slice(None), *[slice(int(si), int(si) + int(ti)) for si, ti in zip(s, patch)]]) for s in starts]
+
+    def _gaussian(self, patch) -> Optional[torch.Tensor]:
+        if not self.use_gaussian:
+            return None
+        key = (tuple(patch), str(self.device))
+        if key not in self._gauss_cache:
+            g = sw.compute_gaussian(tuple(patch), sigma_scale=1. / 8, value_scaling_factor=10, dtype=np.float16)
+            self._gauss_cache = {key: torch.from_numpy(g).to(self.device)}
+        return self._gauss_cache[key]
+
+    def _choose_tiles_per_batch(self, n_flips: int, n_tiles: int) -> int:
+        if self.tiles_per_batch is not None:
+            return max(1, min(int(self.tiles_per_batch), n_tiles))
+        return max(1, min(n_tiles, max(1, 8 // n_flips)))
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.inference_mode()
+    def _sliding_window_accumulate(self, data: torch.Tensor, starts: np.ndarray, acc: torch.Tensor,
+                                   acc_origin=(0, 0, 0)):
+        """Runs every tile in `starts` (volume coordinates) and adds its weighted prediction into `acc`,
+        whose voxel (0,0,0) sits at volume coordinate `acc_origin`."""
+        patch = tuple(self.configuration_manager.patch_size)
+        flips = self._flip_masks()
+        nf = len(flips)
+        tpb = self._choose_tiles_per_batch(nf, len(starts))
+        eng = self.network.engine(self.device, tpb * nf)
+        prog = eng.program
+        heads = self.label_manager.num_segmentation_heads
+        assert prog.num_heads == heads
+        gauss = self._gaussian(patch)
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        starts_dev = torch.from_numpy(starts).to(self.device)
+        local = starts - np.asarray(acc_origin, dtype=np.int32)[None]
+        in_ptr = eng.buffer_ptr(prog.input_buffer)
+        out_ptr = eng.buffer_ptr(prog.output_buffer)
+        in_cs = prog.buffers[prog.input_buffer][1]
+        out_cs = prog.buffers[prog.output_buffer][1]
+        launches = 0
+        for i in range(0, len(starts), tpb):
+            n = min(tpb, len(starts) - i)
+            E.gather_tiles(data, starts_dev[i:i + n], n, patch, flips, in_ptr, in_cs)
+            eng.forward(n * nf)
+            E.accumulate_tiles(out_ptr, _lib.IN_F16, out_cs, heads, local[i:i + n], patch, flips, gauss, acc)
+            launches += 1 + eng.launch_counts()[0] + n
+        self.last_launches += launches
+
+    @torch.inference_mode()
+    def _internal_predict_sliding_window_return_logits(self, data: torch.Tensor, slicers,
+                                                       do_on_device: bool = True, return_labels: bool = False):
+        if not do_on_device:
+            raise RuntimeError('the B200 engine keeps the result arrays on the device; there is no CPU results path')
+        patch = tuple(self.configuration_manager.patch_size)
+        heads = self.label_manager.num_segmentation_heads
+        data = data.to(self.device, dtype=torch.float32).contiguous()
+        vol = tuple(data.shape[1:])
+        starts = np.asarray([[s.start for s in sl[1:]] for sl in slicers], dtype=np.int32)
+        acc = torch.zeros((heads, *vol), dtype=self.accumulator_dtype, device=self.device)
+        self._sliding_window_accumulate(data, starts, acc)
+        wsum = torch.empty(vol, dtype=self.accumulator_dtype, device=self.device)
+        steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
+        E.weight_sum(steps, patch, self._gaussian(patch), wsum)
+        inf_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        logits = torch.empty((heads, *vol), dtype=torch.float16, device=self.device)
+        labels = torch.empty(vol, dtype=torch.uint8, device=self.device) if return_labels else None
+        E.finalize(acc, wsum, logits, labels, inf_flag)
+        self.last_launches += 2
+        del acc, wsum
+        if int(inf_flag.item()) != 0:
+            raise RuntimeError('Encountered inf in predicted array. Aborting... If this problem persists, '
+                               'reduce value_scaling_factor in compute_gaussian or increase the dtype of '
+                               'predicted_logits to fp32')
+        return (logits, labels) if return_labels else logits
+
+    def _check_ready(self, input_image):
+        assert isinstance(input_image, torch.Tensor)
+        if self.network is None:
+            raise RuntimeError('predictor is not initialised')
+        E.require_cuda_device(self.device)
+        assert input_image.ndim == 4, 'input_image must be a 4D np.ndarray or torch.Tensor (c, x, y, z)'
+
+    def _pad(self, input_image: torch.Tensor):
+        patch = self.configuration_manager.patch_size
+        below, above = sw.pad_amounts(input_image.shape[1:], patch)
+        data = input_image.to(self.device, dtype=torch.float32)
+        if any(b or a for b, a in zip(below, above)):
+            pad = []
+            for b, a in zip(below[::-1], above[::-1]):
+                pad += [b, a]
+            data = torch.nn.functional.pad(data, pad, mode='constant', value=0)
+        slicer = tuple(slice(b, b + s) for b, s in zip(below, input_image.shape[1:]))
+        return data.contiguous(), slicer
+
+    @torch.inference_mode()
+    def predict_sliding_window_return_logits(self, input_image: torch.Tensor) -> torch.Tensor:
+        self._check_ready(input_image)
+        self.network = self.network.to(self.device)
+        self.network.eval()
+        self.last_launches = 0
+        if self.verbose:
+            print(f'Input shape: {input_image.shape}')
+            print('step_size:', self.tile_step_size)
+            print('mirror_axes:', self.allowed_mirroring_axes if self.use_mirroring else None)
+        with torch.cuda.device(self.device):
+            data, slicer_revert_padding = self._pad(input_image)
+            slicers = self._internal_get_sliding_window_slicers(data.shape[1:])
+            predicted_logits = self._internal_predict_sliding_window_return_logits(data, slicers, True)
+            predicted_logits = predicted_logits[(slice(None), *slicer_revert_padding)]
+        return predicted_logits
+
+    @torch.inference_mode()
+    def predict_sliding_window_return_segmentation(self, input_image: torch.Tensor) -> torch.Tensor:
+        """Extension: label map (uint8, on device) with the argmax fused into the normalisation pass, so
+        the (heads, x, y, z) logits never cross PCIe.  Equals
+        label_manager.convert_logits_to_segmentation(predict_sliding_window_return_logits(x))."""
+        self._check_ready(input_image)
+        assert not self.label_manager.has_regions, 'region-based label maps go through the logits path'
+        self.network = self.network.to(self.device)
+        self.last_launches = 0
+        with torch.cuda.device(self.device):
+            data, slicer_revert_padding = self._pad(input_image)
+            slicers = self._internal_get_sliding_window_slicers(data.shape[1:])
+            _, labels = self._internal_predict_sliding_window_return_logits(data, slicers, True, return_labels=True)
+            return labels[slicer_revert_padding]
+
+    @torch.inference_mode()
+    def predict_logits_from_preprocessed_data(self, data: torch.Tensor) -> torch.Tensor:
+        """Fold loop of the reference (:471-504); returns the fold-averaged logits on the CPU."""
+        prediction = None
+        for params in self.list_of_parameters:
+            self.network.load_state_dict(params)
+            if prediction is None:
+                prediction = self.predict_sliding_window_return_logits(data).to('cpu')
+            else:
+                prediction += self.predict_sliding_window_return_logits(data).to('cpu')
+        if len(self.list_of_parameters) > 1:
+            prediction /= len(self.list_of_parameters)
+        if self.verbose:
+            print('Prediction done')
+        return prediction
+
+    def predict_single_npy_array(self, input_image: np.ndarray, image_properties: dict,
+                                 segmentation_previous_stage: np.ndarray = None,
+                                 output_file_truncated: str = None,
+                                 save_or_return_probabilities: bool = False):
+        """Array-in / label-map-out entry (:423-468).  Pre- and post-processing around the hot path are
+        host-side steps outside this engine's scope; the subset implemented in
+        `fast_nnunet_b200.prepost` covers images already at the plans' spacing."""
+        from . import prepost
+        if output_file_truncated is not None:
+            raise NotImplementedError('file export is outside the B200 inference path (SURVEY.md §8 f1)')
+        data, props = prepost.preprocess_npy(input_image, image_properties, segmentation_previous_stage,
+                                             self.plans_manager, self.configuration_manager, self.dataset_json,
+                                             self.label_manager)
+        logits = self.predict_logits_from_preprocessed_data(torch.from_numpy(data))
+        return prepost.logits_to_segmentation_with_correct_shape(logits, props, self.plans_manager,
+                                                                 self.label_manager, save_or_return_probabilities)

@@ -1,0 +1,100 @@
+"""GPU parity of the per-patch network forward (libfnnu engine) against the oracle network.
+
+Tolerances (stated, per north_star): the engine stores activations in fp16 with fp32 accumulation and
+fp64 InstanceNorm sums; the oracle runs fp32.  Logits are O(1); we require max|d| <= 0.08 and
+mean|d| <= 0.01 against the fp32 oracle for the shallow test nets, and every intermediate raw conv
+output within 2% of its dynamic range."""
+import numpy as np
+import pytest
+import torch
+
+import nets
+from fast_nnunet_b200 import _lib
+from fast_nnunet_b200.predictor import CompiledNetwork
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda', 0)
+
+
+def _run(spec, batch, backend, seed=0):
+    sd, net = nets.make(spec)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((batch, spec['in_ch'], *spec['patch']), generator=g)
+    cn = CompiledNetwork(spec['cls'], spec['kw'], spec['in_ch'], spec['heads'], spec['patch'])
+    cn.load_state_dict(sd)
+    eng = cn.engine(DEV, batch)
+    eng.set_backend(backend)
+    got = cn(x.to(DEV)).float().cpu()
+    with torch.no_grad():
+        want = net(x.half().float())       # the engine sees the fp16-rounded input
+    return got, want, eng
+
+
+@pytest.mark.parametrize('name', ['SMALL_PLAIN', 'SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC'])
+@pytest.mark.parametrize('backend', [1, 0])
+def test_forward_matches_oracle(name, backend):
+    spec = getattr(nets, name)
+    got, want, eng = _run(spec, 3, backend)
+    assert got.shape == want.shape
+    d = (got - want).abs()
+    scale = want.abs().max().item()
+    print(f'{name} backend={backend}: max|d|={d.max():.4f} mean|d|={d.mean():.5f} logit range={scale:.2f} '
+          f'launches={eng.launch_counts()}')
+    assert torch.isfinite(got).all()
+    assert d.max().item() <= 0.08 * max(1.0, scale / 4)
+    assert d.mean().item() <= 0.01 * max(1.0, scale / 4)
+
+
+def test_batch_entries_are_independent():
+    """InstanceNorm statistics are per (sample, channel): a sample's output must not depend on its batch-mates."""
+    spec = nets.SMALL_PLAIN16
+    sd, _ = nets.make(spec)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((4, 1, *spec['patch']), generator=g).to(DEV)
+    cn = CompiledNetwork(spec['cls'], spec['kw'], 1, 2, spec['patch'])
+    cn.load_state_dict(sd)
+    full = cn(x)
+    single = cn(x[2:3])
+    d = (full[2:3].float() - single.float()).abs().max().item()
+    assert d <= 2e-2, d      # only the order of the fp64 atomic sums may differ
+
+
+def test_intermediate_buffers_and_stats():
+    """First encoder conv: raw output and its InstanceNorm sums against torch."""
+    spec = nets.SMALL_PLAIN16
+    sd, net = nets.make(spec)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 1, *spec['patch']), generator=g)
+    cn = CompiledNetwork(spec['cls'], spec['kw'], 1, 2, spec['patch'])
+    cn.load_state_dict(sd)
+    cn(x.to(DEV))
+    eng = cn.engine(DEV, 2)
+    op0 = eng.program.ops[0]
+    raw = eng.buffer_tensor(op0.dst, 2)[..., op0.dst_coff:op0.dst_coff + op0.cout].float().cpu()
+    conv = net.encoder.stages[0][0].convs[0].conv
+    with torch.no_grad():
+        want = conv(x.half().float()).permute(0, 2, 3, 4, 1)
+    assert (raw - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+    st = eng.stats_tensor(op0.dst, 2)[:, op0.dst_coff:op0.dst_coff + op0.cout].cpu()
+    s1 = raw.double().sum(dim=(1, 2, 3))
+    s2 = (raw.double() ** 2).sum(dim=(1, 2, 3))
+    assert torch.allclose(st[..., 0], s1, rtol=1e-9, atol=1e-6)
+    assert torch.allclose(st[..., 1], s2, rtol=1e-9, atol=1e-6)
+
+
+def test_student_128_forward_matches_oracle():
+    """Full-size distilled student (r=2) on one 128^3 patch x 2 flips; the oracle side takes ~3 s on CPU."""
+    spec = nets.STUDENT
+    sd, net = nets.make(spec, randomize_affine=False)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 1, 128, 128, 128), generator=g)
+    cn = CompiledNetwork(spec['cls'], spec['kw'], 1, 2, spec['patch'])
+    cn.load_state_dict(sd)
+    got = cn(x.to(DEV)).float().cpu()
+    with torch.no_grad():
+        want = net.to(DEV)(x.half().float().to(DEV)).cpu()      # fp32 oracle network, run on the GPU for speed
+    d = (got - want).abs()
+    agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+    print(f'student128: max|d|={d.max():.4f} mean|d|={d.mean():.5f} range={want.abs().max():.2f} argmax agreement={agree:.5f}')
+    assert d.max().item() <= 0.15 and d.mean().item() <= 0.01
+    assert agree >= 0.99
