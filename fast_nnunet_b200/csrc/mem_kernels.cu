@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) weight_sum_kernel(StepLists st, int pX, i
 template <typename AccT>
 __global__ void __launch_bounds__(256) finalize_kernel(const AccT* __restrict__ acc,
                                                        const AccT* __restrict__ wsum, int heads,
-                                                       size_t nvox, __half* __restrict__ logits,
+                                                       size_t nvox, size_t hs, __half* __restrict__ logits,
                                                        uint8_t* __restrict__ labels,
                                                        int32_t* __restrict__ inf_flag) {
   bool saw_inf = false;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const AccT* __restrict__ 
     float best = 0.f;
     int arg = 0;
     for (int h = 0; h < heads; ++h) {
-      float v = __fdiv_rn(to_f<AccT>(acc[(size_t)h * nvox + i]), w);
+      float v = __fdiv_rn(to_f<AccT>(acc[(size_t)h * hs + i]), w);
       __half hv = __float2half_rn(v);
       float r = __half2float(hv);
       if (isinf(r)) saw_inf = true;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const AccT* __restrict__ 
 // 2 heads, fp32 accumulators, nvox % 4 == 0: 128-bit loads, 64-bit logit stores, 32-bit label stores.
 __global__ void __launch_bounds__(256) finalize_h2_vec4_kernel(const float* __restrict__ acc,
                                                                const float* __restrict__ wsum,
-                                                               size_t nvox, __half* __restrict__ logits,
+                                                               size_t nvox, size_t hs, __half* __restrict__ logits,
                                                                uint8_t* __restrict__ labels,
                                                                int32_t* __restrict__ inf_flag) {
   bool saw_inf = false;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) finalize_h2_vec4_kernel(const float* __re
        q += (size_t)gridDim.x * blockDim.x) {
     float4 w = __ldg(reinterpret_cast<const float4*>(wsum) + q);
     float4 a0 = __ldg(reinterpret_cast<const float4*>(acc) + q);
-    float4 a1 = __ldg(reinterpret_cast<const float4*>(acc + nvox) + q);
+    float4 a1 = __ldg(reinterpret_cast<const float4*>(acc + hs) + q);
     float wv[4] = {w.x, w.y, w.z, w.w};
     float v0[4] = {a0.x, a0.y, a0.z, a0.w};
     float v1[4] = {a1.x, a1.y, a1.z, a1.w};
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(256) finalize_h2_vec4_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ acc,
-                                                          const float* __restrict__ other, size_t n) {
-  const size_t nq = n >> 2;
+                                                          const float* __restrict__ other, size_t n, int aligned) {
+  const size_t nq = aligned ? (n >> 2) : 0;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
        q += (size_t)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<float4*>(acc)[q];
@@ -409,24 +409,26 @@ extern "C" int fnnu_weight_sum(const int32_t* steps_x, int nx, const int32_t* st
 }
 
 extern "C" int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, int heads,
-                             const int vol_dims[3], void* logits_out, uint8_t* labels_out,
-                             int32_t* inf_flag_dev, void* stream) {
+                             const int vol_dims[3], size_t acc_head_stride, void* logits_out,
+                             uint8_t* labels_out, int32_t* inf_flag_dev, void* stream) {
   FNNU_CHECK_ARG(acc && wsum && vol_dims, "finalize: null pointer");
   FNNU_CHECK_ARG(heads >= 1 && heads <= 255, "finalize: heads=%d", heads);
   FNNU_CHECK_ARG(acc_dtype == FNNU_ACC_F32 || acc_dtype == FNNU_ACC_F16, "finalize: acc_dtype=%d", acc_dtype);
   size_t nvox = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
+  size_t hs = acc_head_stride ? acc_head_stride : nvox;
+  FNNU_CHECK_ARG(hs >= nvox, "finalize: head stride %zu < %zu voxels", hs, nvox);
   cudaStream_t s = (cudaStream_t)stream;
-  bool vec = acc_dtype == FNNU_ACC_F32 && heads == 2 && nvox % 4 == 0 && ((uintptr_t)acc % 16 == 0) &&
+  bool vec = acc_dtype == FNNU_ACC_F32 && heads == 2 && nvox % 4 == 0 && hs % 4 == 0 && ((uintptr_t)acc % 16 == 0) &&
              ((uintptr_t)wsum % 16 == 0) && (!logits_out || (uintptr_t)logits_out % 8 == 0) &&
              (!labels_out || (uintptr_t)labels_out % 4 == 0);
   if (vec)
-    finalize_h2_vec4_kernel<<<grid_for(nvox / 4, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, nvox,
+    finalize_h2_vec4_kernel<<<grid_for(nvox / 4, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, nvox, hs,
                                                                     (__half*)logits_out, labels_out, inf_flag_dev);
   else if (acc_dtype == FNNU_ACC_F32)
-    finalize_kernel<float><<<grid_for(nvox, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, heads, nvox,
+    finalize_kernel<float><<<grid_for(nvox, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, heads, nvox, hs,
                                                                (__half*)logits_out, labels_out, inf_flag_dev);
   else
-    finalize_kernel<__half><<<grid_for(nvox, 256), 256, 0, s>>>((const __half*)acc, (const __half*)wsum, heads, nvox,
+    finalize_kernel<__half><<<grid_for(nvox, 256), 256, 0, s>>>((const __half*)acc, (const __half*)wsum, heads, nvox, hs,
                                                                 (__half*)logits_out, labels_out, inf_flag_dev);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
@@ -434,9 +436,9 @@ extern "C" int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, i
 
 extern "C" int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream) {
   FNNU_CHECK_ARG(acc && other, "add_inplace: null pointer");
-  FNNU_CHECK_ARG(((uintptr_t)acc % 16 == 0) && ((uintptr_t)other % 16 == 0), "add_inplace: pointers must be 16-byte aligned");
   if (n == 0) return FNNU_OK;
-  add_inplace_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(acc, other, n);
+  int aligned = ((uintptr_t)acc % 16 == 0) && ((uintptr_t)other % 16 == 0);
+  add_inplace_kernel<<<grid_for(aligned ? n / 4 + 1 : n, 256), 256, 0, (cudaStream_t)stream>>>(acc, other, n, aligned);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }

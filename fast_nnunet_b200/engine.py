@@ -146,19 +146,25 @@ def weight_sum(steps, patch: Sequence[int], gaussian: Optional[torch.Tensor], ws
 
 def finalize(acc: torch.Tensor, wsum: torch.Tensor, logits_out: Optional[torch.Tensor],
              labels_out: Optional[torch.Tensor], inf_flag: torch.Tensor):
+    """acc may be a slab view [H, x0:x1] of a larger accumulator (planes contiguous, heads strided)."""
     lib = _lib.load()
     acc_dtype = _lib.ACC_F32 if acc.dtype == torch.float32 else _lib.ACC_F16
-    assert wsum.dtype == acc.dtype and inf_flag.dtype == torch.int32
+    assert wsum.dtype == acc.dtype and inf_flag.dtype == torch.int32 and wsum.is_contiguous()
+    assert acc[0].is_contiguous() and tuple(wsum.shape) == tuple(acc.shape[1:])
+    head_stride = acc.stride(0) if acc.shape[0] > 1 else 0
     if logits_out is not None:
         assert logits_out.dtype == torch.float16 and logits_out.is_contiguous() and logits_out.shape == acc.shape
     if labels_out is not None:
         assert labels_out.dtype == torch.uint8 and labels_out.is_contiguous()
     _lib.check(lib.fnnu_finalize(_ptr(acc), _ptr(wsum), acc_dtype, acc.shape[0], _lib.i3(acc.shape[1:]),
-                                 _ptr(logits_out), _ptr(labels_out), _ptr(inf_flag), _lib.stream_ptr()))
+                                 head_stride, _ptr(logits_out), _ptr(labels_out), _ptr(inf_flag),
+                                 _lib.stream_ptr()))
 
 
 def add_inplace(acc: torch.Tensor, other: torch.Tensor):
     lib = _lib.load()
     assert acc.dtype == torch.float32 and other.dtype == torch.float32 and acc.numel() == other.numel()
     assert acc.is_contiguous() and other.is_contiguous()
+    if acc.numel() == 0:
+        return
     _lib.check(lib.fnnu_add_inplace_f32(_ptr(acc), _ptr(other), acc.numel(), _lib.stream_ptr()))

@@ -80,9 +80,12 @@ int fnnu_weight_sum(const int32_t* steps_x, int nx, const int32_t* steps_y, int 
 /* Replaces `torch.div(predicted_logits, n_predictions, out=...)`, the inf check (:620-625) and
  * LabelManager.convert_logits_to_segmentation (label_handling.py:184-195: argmax over heads, first
  * maximum wins).  logits_out (fp16 [H][X][Y][Z]) and labels_out (uint8 [X][Y][Z]) may each be NULL.
- * inf_flag_dev: device int32, set to 1 if any normalised logit is +-inf (checked by the caller). */
+ * inf_flag_dev: device int32, set to 1 if any normalised logit is +-inf (checked by the caller).
+ * acc_head_stride: elements between consecutive heads of acc (0 = dense, X*Y*Z), so that a slab view
+ * of a larger accumulator can be normalised in place; wsum and the outputs are dense over vol_dims. */
 int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, int heads, const int vol_dims[3],
-                  void* logits_out, uint8_t* labels_out, int32_t* inf_flag_dev, void* stream);
+                  size_t acc_head_stride, void* logits_out, uint8_t* labels_out, int32_t* inf_flag_dev,
+                  void* stream);
 
 /* Multi-GPU halo step: acc += other over a contiguous range of n elements (fp32). */
 int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream);
