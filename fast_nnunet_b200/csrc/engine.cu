@@ -300,7 +300,7 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       a.w = wd;
       if (p.w_umma_bytes[i]) {
         void* wu = pa + p.w_umma_off[i];
-        rc = launch_pack_weights_umma(staging, wu, o.cin, o.cout, a.transposed ? o.stride : o.kernel, a.transposed, s);
+        rc = launch_pack_weights_umma(staging, wu, a, s);
         if (rc) { delete e; return rc; }
         a.w_umma = wu;
       }

@@ -58,8 +58,7 @@ int launch_avgpool(const EltArgs& a, cudaStream_t s);
 // tcgen05 implicit-GEMM back end (conv_umma.cu)
 bool umma_supported(const ConvArgs& a);
 size_t umma_packed_weight_bytes(int cin, int cout, int ntaps, int transposed);
-int launch_pack_weights_umma(const float* w_dev, void* out, int cin, int cout, const int k[3], int transposed,
-                             cudaStream_t s);
+int launch_pack_weights_umma(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_umma(const ConvArgs& a, cudaStream_t s);
 
 }  // namespace fnnu

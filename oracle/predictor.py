@@ -16,7 +16,7 @@ import itertools
 import numpy as np
 import torch
 
-from .sliding_window import gaussian_map, pad_to_patch, slicers_for
+from .sliding_window import gaussian_map, pad_to_patch, slicers_for  # noqa: F401 (pad_to_patch re-exported)
 
 
 def mirror_axes_combinations(mirror_axes):
@@ -61,10 +61,12 @@ def accumulate_tiles(tile_predictions, slicers, volume_shape, num_heads, patch_s
 @torch.inference_mode()
 def predict_sliding_window_return_logits(network, input_image, patch_size, tile_step_size=0.5, use_gaussian=True,
                                          mirror_axes=(0, 1, 2), tile_subset=None, return_tile_predictions=False,
-                                         autocast_device=None):
+                                         autocast_device=None, acc_dtype=torch.half, return_n_predictions=False):
     """predict_from_raw_data.py:634-680 (CPU semantics: fp32 network, fp16 accumulators; pass
     autocast_device='cuda' with a CUDA network/input for the reference's GPU semantics).
-    `tile_subset` restricts the loop to some tile indices (bounded CPU-baseline samples)."""
+    `tile_subset` restricts the loop to some tile indices (bounded CPU-baseline samples).
+    `acc_dtype=torch.float32` is NOT the reference's arithmetic: it is the exact-accumulation variant used
+    to separate network error from the reference's fp16-accumulator noise in the parity report."""
     assert isinstance(input_image, torch.Tensor) and input_image.ndim == 4
     network.eval()
     ctx = torch.autocast(autocast_device, enabled=True) if autocast_device else _Null()
@@ -82,8 +84,8 @@ def predict_sliding_window_return_logits(network, input_image, patch_size, tile_
             pred = mirror_and_predict(network, workon, mirror_axes)[0]
             if logits is None:
                 heads = pred.shape[0]
-                logits = torch.zeros((heads, *data.shape[1:]), dtype=torch.half, device=data.device)
-                n_pred = torch.zeros(data.shape[1:], dtype=torch.half, device=data.device)
+                logits = torch.zeros((heads, *data.shape[1:]), dtype=acc_dtype, device=data.device)
+                n_pred = torch.zeros(data.shape[1:], dtype=acc_dtype, device=data.device)
             if return_tile_predictions:
                 tile_preds.append(pred.clone())
             if use_gaussian:
@@ -95,8 +97,11 @@ def predict_sliding_window_return_logits(network, input_image, patch_size, tile_
             if torch.any(torch.isinf(logits)):
                 raise RuntimeError('Encountered inf in predicted array.')
         logits = logits[(slice(None), *revert[1:])]
+        n_pred = n_pred[tuple(revert[1:])]
     if return_tile_predictions:
         return logits, tile_preds, slicers
+    if return_n_predictions:
+        return logits, n_pred
     return logits
 
 

@@ -98,3 +98,37 @@ def test_student_128_forward_matches_oracle():
     print(f'student128: max|d|={d.max():.4f} mean|d|={d.mean():.5f} range={want.abs().max():.2f} argmax agreement={agree:.5f}')
     assert d.max().item() <= 0.15 and d.mean().item() <= 0.01
     assert agree >= 0.99
+
+
+@pytest.mark.parametrize('name', ['SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC'])
+def test_tcgen05_layers_match_direct_kernel(name):
+    """Every activation buffer written with the tcgen05 implicit-GEMM back end against the CUDA-core direct
+    kernel (same fp16 inputs, fp32 accumulation in both): differences are fp32 summation order + one fp16 ulp."""
+    spec = getattr(nets, name)
+    sd, _ = nets.make(spec)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((3, spec['in_ch'], *spec['patch']), generator=g).to(DEV)
+    cn = CompiledNetwork(spec['cls'], spec['kw'], spec['in_ch'], spec['heads'], spec['patch'])
+    cn.load_state_dict(sd)
+    eng = cn.engine(DEV, 3)
+    eng.set_backend(1)
+    cn(x)
+    ref = [eng.buffer_tensor(i, 3).float().clone() for i in range(len(eng.program.buffers))]
+    ref_stats = [eng.stats_tensor(i, 3).clone() for i in range(len(eng.program.buffers))]
+    eng.set_backend(0)
+    cn(x)
+    total, umma = eng.launch_counts()
+    assert umma > 0, 'no layer ran on the tcgen05 back end'
+    worst = 0.0
+    for op in eng.program.ops:
+        got = eng.buffer_tensor(op.dst, 3).float()[..., op.dst_coff:op.dst_coff + op.cout]
+        want = ref[op.dst][..., op.dst_coff:op.dst_coff + op.cout]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs().max().item() / scale
+        worst = max(worst, err)
+        assert err <= 4e-3, f'{op.name}: relative error {err:.5f} (cin={op.cin} cout={op.cout} k={op.kernel} s={op.stride})'
+        if op.has_norm:
+            st = eng.stats_tensor(op.dst, 3)[:, op.dst_coff:op.dst_coff + op.cout]
+            rs = ref_stats[op.dst][:, op.dst_coff:op.dst_coff + op.cout]
+            assert torch.allclose(st, rs, rtol=2e-3, atol=1e-1), f'{op.name}: InstanceNorm sums differ'
+    print(f'{name}: {umma}/{total} launches on tcgen05, worst relative layer error {worst:.2e}')

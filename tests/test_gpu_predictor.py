@@ -18,23 +18,45 @@ def _folder(tmp_path, spec, sd, **kw):
                                 spec['patch'], sd, spec['in_ch'], spec['heads'], **kw)
 
 
-def _compare(got_logits, want_logits, heads, tol_max, tol_mean):
+def _oracle(net, x, patch, use_gaussian=True, mirror_axes=(0, 1, 2)):
+    """Reference arithmetic (fp16 accumulators) and the exact-accumulation variant from ONE set of oracle
+    tile predictions."""
+    _, tile_preds, slicers = OP.predict_sliding_window_return_logits(net, x, patch, 0.5, use_gaussian, mirror_axes,
+                                                                     return_tile_predictions=True)
+    xp, revert = OP.pad_to_patch(x, patch)
+    heads = tile_preds[0].shape[0]
+    ref16, n16 = OP.accumulate_tiles(tile_preds, slicers, tuple(xp.shape[1:]), heads, patch, use_gaussian, torch.half)
+    ref32, _ = OP.accumulate_tiles(tile_preds, slicers, tuple(xp.shape[1:]), heads, patch, use_gaussian, torch.float32)
+    crop = (slice(None), *revert[1:])
+    return ref16[crop], n16[tuple(revert[1:])], ref32[crop]
+
+
+def _compare(got_logits, oracle, heads, tol_max=0.06, tol_mean=0.006):
+    """Parity statement:
+      (1) against the oracle with exact (fp32) accumulation: max / mean |d| of the normalised logits on ALL voxels;
+      (2) against the reference arithmetic (fp16 accumulators): the same on the voxels whose weight sum is a normal
+          fp16 number (n_predictions >= 6.1e-5; below that the reference's own accumulators hold 1-2 significant bits);
+      (3) label agreement on all voxels, and on voxels whose top-2 margin exceeds 4 x tol_max it must be total."""
+    ref16, n16, ref32 = oracle
     got = got_logits.float().cpu()
-    want = want_logits.float().cpu()
-    d = (got - want).abs()
-    seg_g = OP.logits_to_segmentation(got)
-    seg_w = OP.logits_to_segmentation(want)
-    agree = float((seg_g == seg_w).mean())
-    top2 = torch.topk(want, 2, dim=0).values
-    margin = (top2[0] - top2[1]).numpy()
-    confident = margin > 2 * tol_max
-    agree_conf = float((seg_g == seg_w)[confident].mean()) if confident.any() else 1.0
-    dice = OP.dice_per_class(seg_g, seg_w, heads)
-    print(f'max|d|={d.max():.4f} mean|d|={d.mean():.5f} agree={agree:.5f} agree(margin>{2 * tol_max})={agree_conf:.6f} '
-          f'({confident.mean():.3f} of voxels) dice={["%.4f" % x for x in dice]}')
-    assert d.max().item() <= tol_max and d.mean().item() <= tol_mean
-    assert agree_conf >= 0.999
-    return agree, dice
+    d32 = (got - ref32.float()).abs()
+    ok16 = (n16.float() >= 6.1e-5)
+    d16 = (got - ref16.float()).abs()[:, ok16]
+    seg_g, seg_32, seg_16 = (OP.logits_to_segmentation(t) for t in (got, ref32, ref16))
+    agree32 = float((seg_g == seg_32).mean())
+    agree16 = float((seg_g == seg_16)[ok16.numpy()].mean())
+    top2 = torch.topk(ref32.float(), 2, dim=0).values
+    confident = ((top2[0] - top2[1]) > 4 * tol_max).numpy()
+    agree_conf = float((seg_g == seg_32)[confident].mean()) if confident.any() else 1.0
+    dice = OP.dice_per_class(seg_g, seg_32, heads)
+    print(f'vs exact-acc oracle: max|d|={d32.max():.4f} mean|d|={d32.mean():.5f} labels agree={agree32:.5f} '
+          f'(confident {confident.mean():.3f} of voxels: {agree_conf:.6f}) dice={["%.4f" % v for v in dice]} | '
+          f'vs fp16-acc reference arithmetic on {float(ok16.float().mean()):.4f} of voxels: max|d|={d16.max():.4f} '
+          f'mean|d|={d16.mean():.5f} labels agree={agree16:.5f}')
+    assert d32.max().item() <= tol_max and d32.mean().item() <= tol_mean
+    assert d16.max().item() <= tol_max + 0.05 and d16.mean().item() <= tol_mean + 0.002
+    assert agree_conf == 1.0
+    assert agree32 >= 0.99
 
 
 @pytest.mark.parametrize('name,vol', [('SMALL_PLAIN16', (48, 40, 56)), ('SMALL_RESENC', (40, 40, 40)),
@@ -48,8 +70,7 @@ def test_sliding_window_matches_oracle(tmp_path, name, vol):
     p.initialize_from_trained_model_folder(folder, use_folds=(0,))
     got = p.predict_sliding_window_return_logits(x)
     assert got.dtype == torch.float16 and tuple(got.shape) == (spec['heads'], *vol) and got.device.type == 'cuda'
-    want = OP.predict_sliding_window_return_logits(net, x.half().float(), spec['patch'], 0.5, True, (0, 1, 2))
-    _compare(got, want, spec['heads'], 0.1, 0.012)
+    _compare(got, _oracle(net, x.half().float(), spec['patch']), spec['heads'])
     labels = p.predict_sliding_window_return_segmentation(x)
     assert np.array_equal(labels.cpu().numpy(), OP.logits_to_segmentation(got).astype(np.uint8))
     assert p.last_launches > 0
@@ -64,8 +85,7 @@ def test_small_volume_is_padded(tmp_path):
     p.initialize_from_trained_model_folder(folder, use_folds=None)
     got = p.predict_sliding_window_return_logits(x)
     assert tuple(got.shape) == (2, 20, 33, 30)
-    want = OP.predict_sliding_window_return_logits(net, x.half().float(), spec['patch'], 0.5, True, (0, 1, 2))
-    _compare(got, want, 2, 0.1, 0.012)
+    _compare(got, _oracle(net, x.half().float(), spec['patch']), 2)
 
 
 def test_no_mirroring_no_gaussian_and_fp16_accumulators(tmp_path):
@@ -78,8 +98,7 @@ def test_no_mirroring_no_gaussian_and_fp16_accumulators(tmp_path):
     p.initialize_from_trained_model_folder(folder, use_folds=(0,))
     assert p.allowed_mirroring_axes is None
     got = p.predict_sliding_window_return_logits(x)
-    want = OP.predict_sliding_window_return_logits(net, x.half().float(), spec['patch'], 0.5, False, None)
-    _compare(got, want, 2, 0.1, 0.012)
+    _compare(got, _oracle(net, x.half().float(), spec['patch'], False, None), 2)
 
 
 def test_fold_ensemble_and_cpu_return(tmp_path):
@@ -94,10 +113,10 @@ def test_fold_ensemble_and_cpu_return(tmp_path):
     assert len(p.list_of_parameters) == 2
     got = p.predict_logits_from_preprocessed_data(x)
     assert got.device.type == 'cpu'
-    w0 = OP.predict_sliding_window_return_logits(net0, x.half().float(), spec['patch'], 0.5, True, (0, 1, 2))
-    w1 = OP.predict_sliding_window_return_logits(net1, x.half().float(), spec['patch'], 0.5, True, (0, 1, 2))
-    want = (w0 + w1) / 2
-    _compare(got, want, 2, 0.1, 0.012)
+    o0 = _oracle(net0, x.half().float(), spec['patch'])
+    o1 = _oracle(net1, x.half().float(), spec['patch'])
+    both = ((o0[0].float() + o1[0].float()) / 2, torch.minimum(o0[1], o1[1]), (o0[2] + o1[2]) / 2)
+    _compare(got, both, 2)
 
 
 def test_manual_initialization_with_live_module(tmp_path):
@@ -112,8 +131,7 @@ def test_manual_initialization_with_live_module(tmp_path):
     p.manual_initialization(net, pm, pm.get_configuration('3d_fullres'), None, dj, 'nnUNetTrainer', (0, 1, 2))
     x = nets.ct_like_volume((32, 32, 48), 1)
     got = p.predict_sliding_window_return_logits(x)
-    want = OP.predict_sliding_window_return_logits(net, x.half().float(), spec['patch'], 0.5, True, None)
-    _compare(got, want, 2, 0.1, 0.012)
+    _compare(got, _oracle(net, x.half().float(), spec['patch'], True, None), 2)
 
 
 def test_predict_single_npy_array(tmp_path):
