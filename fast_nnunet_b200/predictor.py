@@ -145,6 +145,9 @@ class nnUNetPredictor(object):
         self.accumulator_dtype = accumulator_dtype
         self.tiles_per_batch = tiles_per_batch
         self.last_launches = 0          # kernels launched by the last predict_* call (bench evidence)
+        self.last_tiles_per_batch = None
+        self.collect_timing = False     # bench: CUDA events around each phase of the tile loop
+        self.timing = {}
         self._gauss_cache = {}
 
     # ------------------------------------------------------------------ model loading
@@ -297,13 +300,42 @@ class nnUNetPredictor(object):
         in_cs = prog.buffers[prog.input_buffer][1]
         out_cs = prog.buffers[prog.output_buffer][1]
         launches = 0
+        self.last_tiles_per_batch = tpb
         for i in range(0, len(starts), tpb):
             n = min(tpb, len(starts) - i)
+            self._mark('gather')
             E.gather_tiles(data, starts_dev[i:i + n], n, patch, flips, in_ptr, in_cs)
+            self._mark('forward')
             eng.forward(n * nf)
+            self._mark('accumulate')
             E.accumulate_tiles(out_ptr, _lib.IN_F16, out_cs, heads, local[i:i + n], patch, flips, gauss, acc)
+            self._mark(None)
             launches += 1 + eng.launch_counts()[0] + n
         self.last_launches += launches
+
+    # ------------------------------------------------------------------ phase timing (bench only)
+    def _mark(self, phase):
+        """Closes the running phase and opens `phase` with CUDA events on the launching stream."""
+        if not self.collect_timing:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        cur = self.timing.get('_open')
+        if cur is not None:
+            self.timing.setdefault(cur[0], []).append((cur[1], ev))
+        self.timing['_open'] = (phase, ev) if phase is not None else None
+
+    def timing_summary(self):
+        """ms per phase summed over everything recorded since `timing` was reset, divided by the number of
+        volumes (calls of the tile loop's owner)."""
+        torch.cuda.synchronize()
+        out = {}
+        n = max(1, self.timing.get('_volumes', 1))
+        for k, pairs in self.timing.items():
+            if k.startswith('_'):
+                continue
+            out[k + '_ms'] = sum(a.elapsed_time(b) for a, b in pairs) / n
+        return out
 
     @torch.inference_mode()
     def _internal_predict_sliding_window_return_logits(self, data: torch.Tensor, slicers,
@@ -315,15 +347,20 @@ class nnUNetPredictor(object):
         data = data.to(self.device, dtype=torch.float32).contiguous()
         vol = tuple(data.shape[1:])
         starts = np.asarray([[s.start for s in sl[1:]] for sl in slicers], dtype=np.int32)
+        if self.collect_timing:
+            self.timing['_volumes'] = self.timing.get('_volumes', 0) + 1
         acc = torch.zeros((heads, *vol), dtype=self.accumulator_dtype, device=self.device)
         self._sliding_window_accumulate(data, starts, acc)
+        self._mark('weight_sum')
         wsum = torch.empty(vol, dtype=self.accumulator_dtype, device=self.device)
         steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
         E.weight_sum(steps, patch, self._gaussian(patch), wsum)
+        self._mark('finalize')
         inf_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        logits = torch.empty((heads, *vol), dtype=torch.float16, device=self.device)
+        logits = None if return_labels == 'only' else torch.empty((heads, *vol), dtype=torch.float16, device=self.device)
         labels = torch.empty(vol, dtype=torch.uint8, device=self.device) if return_labels else None
         E.finalize(acc, wsum, logits, labels, inf_flag)
+        self._mark(None)
         self.last_launches += 2
         del acc, wsum
         if int(inf_flag.item()) != 0:
@@ -380,8 +417,100 @@ class nnUNetPredictor(object):
         with torch.cuda.device(self.device):
             data, slicer_revert_padding = self._pad(input_image)
             slicers = self._internal_get_sliding_window_slicers(data.shape[1:])
-            _, labels = self._internal_predict_sliding_window_return_logits(data, slicers, True, return_labels=True)
+            _, labels = self._internal_predict_sliding_window_return_logits(data, slicers, True, return_labels='only')
             return labels[slicer_revert_padding]
+
+    @torch.inference_mode()
+    def predict_sliding_window_sharded(self, input_image: torch.Tensor, group=None, return_labels: bool = False,
+                                       gather_to: Optional[int] = 0):
+        """ONE volume across the ranks of `group` (one process per GPU): the tile list is cut into contiguous
+        runs (x-slabs in the reference's tile order), each rank accumulates the planes its tiles touch, the
+        overlapping partial sums are exchanged once (NCCL point-to-point over NVLink) and every rank normalises
+        the planes it owns.  Every rank passes the same `input_image`.  Returns, on rank `gather_to`, the full
+        (heads, x, y, z) fp16 logits (or the uint8 label map if `return_labels`); on other ranks their own slab.
+        With gather_to=None every rank returns (slab, (x_lo, x_hi))."""
+        import torch.distributed as dist
+        from . import sharding
+        self._check_ready(input_image)
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.network = self.network.to(self.device)
+        self.last_launches = 0
+        patch = tuple(self.configuration_manager.patch_size)
+        heads = self.label_manager.num_segmentation_heads
+        with torch.cuda.device(self.device):
+            data, revert = self._pad(input_image)
+            vol = tuple(data.shape[1:])
+            starts = sw.tile_starts(vol, patch, self.tile_step_size)
+            plan = sharding.plan_shards(starts, patch, vol, world)
+            lo, hi = plan.tile_ranges[rank]
+            l0, l1 = plan.local[rank]
+            o0, o1 = plan.owned[rank]
+            if self.collect_timing:
+                self.timing['_volumes'] = self.timing.get('_volumes', 0) + 1
+            acc = torch.zeros((heads, l1 - l0, vol[1], vol[2]), dtype=torch.float32, device=self.device)
+            if hi > lo:
+                self._sliding_window_accumulate(data, starts[lo:hi], acc, acc_origin=(l0, 0, 0))
+            self._mark('exchange')
+            sharding.exchange_halos(acc, plan, rank, E.add_inplace, group)
+            self._mark('weight_sum')
+            n_own = o1 - o0
+            out = None
+            if n_own > 0:
+                wsum = torch.empty((n_own, vol[1], vol[2]), dtype=torch.float32, device=self.device)
+                steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
+                steps = [[s - o0 for s in steps[0]], steps[1], steps[2]]
+                E.weight_sum(steps, patch, self._gaussian(patch), wsum)
+                self._mark('finalize')
+                inf_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+                view = acc[:, o0 - l0:o1 - l0]
+                if return_labels:
+                    out = torch.empty((n_own, vol[1], vol[2]), dtype=torch.uint8, device=self.device)
+                    E.finalize(view, wsum, None, out, inf_flag)
+                else:
+                    out = torch.empty((heads, n_own, vol[1], vol[2]), dtype=torch.float16, device=self.device)
+                    E.finalize(view, wsum, out, None, inf_flag)
+                self.last_launches += 2
+                if int(inf_flag.item()) != 0:
+                    raise RuntimeError('Encountered inf in predicted array.')
+            self._mark('gather_result')
+            if gather_to is None or world == 1:
+                self._mark(None)
+                if world == 1:
+                    return out[revert] if return_labels else out[(slice(None), *revert)]
+                return out, (o0, o1)
+            full = None
+            ops = []
+            if rank == gather_to:
+                full = torch.empty((vol if return_labels else (heads, *vol)),
+                                   dtype=torch.uint8 if return_labels else torch.float16, device=self.device)
+                for r in range(world):
+                    a, b = plan.owned[r]
+                    if b <= a:
+                        continue
+                    if r == rank:
+                        if return_labels:
+                            full[a:b] = out
+                        else:
+                            full[:, a:b] = out
+                    elif return_labels:
+                        ops.append(dist.P2POp(dist.irecv, full[a:b], r, group=group))
+                    else:
+                        for h in range(heads):
+                            ops.append(dist.P2POp(dist.irecv, full[h, a:b], r, group=group))
+            elif n_own > 0:
+                if return_labels:
+                    ops.append(dist.P2POp(dist.isend, out, gather_to, group=group))
+                else:
+                    for h in range(heads):
+                        ops.append(dist.P2POp(dist.isend, out[h], gather_to, group=group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            self._mark(None)
+            if rank == gather_to:
+                return full[revert] if return_labels else full[(slice(None), *revert)]
+            return out
 
     @torch.inference_mode()
     def predict_logits_from_preprocessed_data(self, data: torch.Tensor) -> torch.Tensor:

@@ -130,5 +130,11 @@ def test_tcgen05_layers_match_direct_kernel(name):
         if op.has_norm:
             st = eng.stats_tensor(op.dst, 3)[:, op.dst_coff:op.dst_coff + op.cout]
             rs = ref_stats[op.dst][:, op.dst_coff:op.dst_coff + op.cout]
-            assert torch.allclose(st, rs, rtol=2e-3, atol=1e-1), f'{op.name}: InstanceNorm sums differ'
+            # a few fp16 roundings flip with the fp32 summation order, so compare the implied mean / std
+            n = float(np.prod(eng.program.buffers[op.dst][0]))
+            mean_a, mean_b = st[..., 0] / n, rs[..., 0] / n
+            std_a = (st[..., 1] / n - mean_a ** 2).clamp_min(0).sqrt()
+            std_b = (rs[..., 1] / n - mean_b ** 2).clamp_min(0).sqrt()
+            assert ((mean_a - mean_b).abs() <= 2e-3 * std_b + 1e-6).all(), f'{op.name}: InstanceNorm mean differs'
+            assert ((std_a / std_b - 1).abs() <= 2e-3).all(), f'{op.name}: InstanceNorm std differs'
     print(f'{name}: {umma}/{total} launches on tcgen05, worst relative layer error {worst:.2e}')
