@@ -21,8 +21,15 @@
 // warp 8 MMA issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
 // and MMA; TMEM accumulator buffers (full/empty mbarriers) between MMA and epilogue.
 //
-// Replaces the cuDNN calls behind `self.network(x)` (predict_from_raw_data.py:543) for stride-1
-// Conv3d layers with Cin % 16 == 0; other shapes run on conv_ref.cu.
+// Strided convolutions keep the same structure through a phase decomposition: with stride s the tap k
+// reads input s*(o + d) + a where k - pad = s*d + a, so the producers write one flattened plane per
+// phase a (even / odd rows and columns) and every tap is again a shifted read of one of those planes.
+// ConvTranspose3d with kernel == stride is the 1-tap case with the taps folded into N
+// (N = prod(stride) * Cout) and an epilogue that scatters each 16-channel group to its output voxel.
+//
+// Replaces the cuDNN calls behind `self.network(x)` (predict_from_raw_data.py:543) for Conv3d
+// (kernel 1|3, stride 1|2 per axis) and ConvTranspose3d (kernel == stride) layers with Cin % 16 == 0;
+// other shapes (the 1- or 4-channel first layer) run on conv_ref.cu.
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -30,16 +37,24 @@ namespace fnnu {
 
 struct UmmaCfg {
   int ok;
-  int Nc, n_chunks;       // N per MMA, number of Cout chunks
+  int transposed;
+  int Nc, n_chunks;       // N per MMA, number of (virtual) Cout chunks
+  int cout_virtual;       // conv: cout_pad; transposed: prod(stride) * cout_pad
   int KC, G;              // 16-channel chunks per stage, stage groups per kz
   int TY, n_yblocks, T;   // output rows per unit, units per plane, M-tiles per unit
   int rows_mode, tiles_per_row;
-  int Wp, R, P_fill, P_alloc;
-  int pz, py, px, nkz, nky, nkx;
+  int Dz, Ho, Wo;         // extents of the position space the M-tiles cover (conv: output; transposed: input)
+  int pitch;              // positions per row of a flattened phase plane
+  int lead_y, lead_x;     // leading pad rows / columns of a phase plane
+  int nph_y, nph_x;       // phases per axis (= stride)
+  int R, P_fill, P_plane, P_alloc;   // rows and positions per phase plane; positions per 8-channel group
+  int nkz, pz, sz, sy, sx;
+  int ntyx;
+  int tap_aoff[9];        // per in-plane tap: phase * P_plane + shifted start (positions)
   int stages, a_stage_bytes, b_stage_bytes;
   int tmem_bufs;
   int smem_bytes;
-  unsigned wp_magic;
+  unsigned pitch_magic;
 };
 
 struct UmmaArgs {
@@ -54,70 +69,109 @@ constexpr int kThreadsUmma = 288;
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline int tile_base_of(const UmmaCfg& c, int i) {
-  return c.rows_mode ? (i / c.tiles_per_row) * c.Wp + (i % c.tiles_per_row) * 128 : i * 128;
+  return c.rows_mode ? (i / c.tiles_per_row) * c.pitch + (i % c.tiles_per_row) * 128 : i * 128;
+}
+
+// k - pad = s*d + a  (floor division): tap k reads phase a at index (o + d)
+static inline void tap_split(int k, int pad, int s, int& d, int& a) {
+  int v = k - pad;
+  d = (v >= 0) ? v / s : -((-v + s - 1) / s);
+  a = v - d * s;
 }
 
 static bool plan_umma(const ConvArgs& a, UmmaCfg& c) {
   memset(&c, 0, sizeof(c));
-  if (a.transposed) return false;
-  if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
   if (a.cin % 16 != 0 || a.cin < 16) return false;
   if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
-  const int D = a.in_d[0], H = a.in_d[1], W = a.in_d[2];
-  (void)D;
-  c.nkz = a.k[0]; c.nky = a.k[1]; c.nkx = a.k[2];
-  c.pz = a.pad[0]; c.py = a.pad[1]; c.px = a.pad[2];
-  const int cout_pad = a.cout_pad;
-  if (cout_pad <= 256) {
-    c.Nc = cout_pad;
+  if (a.cout_pad % 16 != 0) return false;
+  c.transposed = a.transposed;
+  int dy[3], ay[3], dx[3], ax[3];
+  int nky, nkx, trail_y = 0, trail_x = 0;
+  if (a.transposed) {
+    c.Dz = a.in_d[0]; c.Ho = a.in_d[1]; c.Wo = a.in_d[2];
+    c.nkz = 1; c.pz = 0; c.sz = 1; c.sy = 1; c.sx = 1;
+    nky = nkx = 1;
+    dy[0] = dx[0] = ay[0] = ax[0] = 0;
+    c.nph_y = c.nph_x = 1;
+    c.cout_virtual = a.ntaps * a.cout_pad;
+  } else {
+    c.Dz = a.out_d[0]; c.Ho = a.out_d[1]; c.Wo = a.out_d[2];
+    c.nkz = a.k[0]; c.pz = a.pad[0]; c.sz = a.s[0]; c.sy = a.s[1]; c.sx = a.s[2];
+    nky = a.k[1]; nkx = a.k[2];
+    for (int k = 0; k < nky; ++k) {
+      tap_split(k, a.pad[1], c.sy, dy[k], ay[k]);
+      if (-dy[k] > c.lead_y) c.lead_y = -dy[k];
+      if (dy[k] > trail_y) trail_y = dy[k];
+    }
+    for (int k = 0; k < nkx; ++k) {
+      tap_split(k, a.pad[2], c.sx, dx[k], ax[k]);
+      if (-dx[k] > c.lead_x) c.lead_x = -dx[k];
+      if (dx[k] > trail_x) trail_x = dx[k];
+    }
+    c.nph_y = c.sy; c.nph_x = c.sx;
+    c.cout_virtual = a.cout_pad;
+  }
+  c.ntyx = nky * nkx;
+  if (c.cout_virtual <= 256) {
+    c.Nc = c.cout_virtual;
   } else {
     c.Nc = 0;
     for (int n = 256; n >= 16; n -= 16)
-      if (cout_pad % n == 0) { c.Nc = n; break; }
+      if (c.cout_virtual % n == 0) { c.Nc = n; break; }
     if (!c.Nc) return false;
   }
-  c.n_chunks = cout_pad / c.Nc;
-  c.Wp = W + 2 * c.px;
-  if (c.Wp >= 65536) return false;
-  c.rows_mode = (W % 128 == 0);
-  c.tiles_per_row = c.rows_mode ? W / 128 : 0;
-  const int ntyx = c.nky * c.nkx;
-  const int misc = 256 + 3 * a.cin * 4 + 2 * c.Nc * 4 + 1024;
+  c.n_chunks = c.cout_virtual / c.Nc;
+  c.pitch = c.Wo + c.lead_x + trail_x;
+  if (c.pitch >= 32768) return false;
+  c.rows_mode = (c.Wo % 128 == 0);
+  c.tiles_per_row = c.rows_mode ? c.Wo / 128 : 0;
+  const int nph = c.nph_y * c.nph_x;
+  const int misc = 512 + 3 * a.cin * 4 + 2 * c.Nc * 4 + 1024;
   const int avail = kSmemLimit - misc;
+  const int center = c.lead_y * c.pitch + c.lead_x;
+  int max_shift = 0;   // largest shifted start (relative to the tile base) over the taps
+  for (int ky = 0; ky < nky; ++ky)
+    for (int kx = 0; kx < nkx; ++kx) {
+      int sft = center + dy[ky] * c.pitch + dx[kx];
+      if (sft > max_shift) max_shift = sft;
+    }
+  auto plane_positions = [&](int ty, int T) {
+    int R = ty + c.lead_y + trail_y;
+    int last_base = c.rows_mode ? ((T - 1) / c.tiles_per_row) * c.pitch + ((T - 1) % c.tiles_per_row) * 128 : (T - 1) * 128;
+    int need = last_base + 128 + max_shift;
+    if (need < R * c.pitch) need = R * c.pitch;
+    return (need + 7) / 8 * 8;
+  };
   double best_cost = 1e30;
   int best_ty = 0;
-  for (int ty = 1; ty <= H; ++ty) {
-    int T = c.rows_mode ? ty * c.tiles_per_row : ((ty - 1) * c.Wp + W + 127) / 128;
-    if (T * c.Nc > 512) break;
-    int R = ty + 2 * c.py;
-    int last_base = c.rows_mode ? ((T - 1) / c.tiles_per_row) * c.Wp + ((T - 1) % c.tiles_per_row) * 128 : (T - 1) * 128;
-    int need = last_base + 128 + (c.nky - 1) * c.Wp + (c.nkx - 1);
-    if (need < R * c.Wp) need = R * c.Wp;
-    int palloc = (need + 7) / 8 * 8 + 4;
-    int stage1 = 2 * palloc * 16 + ntyx * 2 * c.Nc * 16;
+  for (int ty = 1; ty <= c.Ho; ++ty) {
+    int T = c.rows_mode ? ty * c.tiles_per_row : ((ty - 1) * c.pitch + c.Wo + 127) / 128;
+    if (T * c.Nc > 512 || T > 64) break;
+    int palloc = nph * plane_positions(ty, T) + 4;
+    int stage1 = 2 * palloc * 16 + c.ntyx * 2 * c.Nc * 16;
     if (2 * stage1 > avail) break;
-    int nb = (H + ty - 1) / ty;
+    int nb = (c.Ho + ty - 1) / ty;
+    int R = ty + c.lead_y + trail_y;
     double cost = (double)nb * T * (2 * T * c.Nc <= 512 ? 1.0 : 1.06) * (1.0 + 0.15 * (double)(R - ty) / ty);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_ty = ty; }
+    if (cost <= best_cost + 1e-9) { best_cost = cost; best_ty = ty; }   // ties: larger blocks, fewer units
   }
   if (!best_ty) return false;
   c.TY = best_ty;
-  c.n_yblocks = (H + c.TY - 1) / c.TY;
-  c.T = c.rows_mode ? c.TY * c.tiles_per_row : ((c.TY - 1) * c.Wp + W + 127) / 128;
-  c.R = c.TY + 2 * c.py;
-  c.P_fill = c.R * c.Wp;
-  {
-    int last_base = tile_base_of(c, c.T - 1);
-    int need = last_base + 128 + (c.nky - 1) * c.Wp + (c.nkx - 1);
-    if (need < c.P_fill) need = c.P_fill;
-    c.P_alloc = (need + 7) / 8 * 8 + 4;
-  }
+  c.n_yblocks = (c.Ho + c.TY - 1) / c.TY;
+  c.T = c.rows_mode ? c.TY * c.tiles_per_row : ((c.TY - 1) * c.pitch + c.Wo + 127) / 128;
+  c.R = c.TY + c.lead_y + trail_y;
+  c.P_fill = c.R * c.pitch;
+  c.P_plane = plane_positions(c.TY, c.T);
+  c.P_alloc = nph * c.P_plane + 4;     // +4: plane stride = 64 mod 128 bytes (fewer st.shared bank conflicts)
+  for (int ky = 0; ky < nky; ++ky)
+    for (int kx = 0; kx < nkx; ++kx)
+      c.tap_aoff[ky * nkx + kx] = (ay[ky] * c.nph_x + ax[kx]) * c.P_plane + center + dy[ky] * c.pitch + dx[kx];
   c.tmem_bufs = (2 * c.T * c.Nc <= 512) ? 2 : 1;
   const int chunks = a.cin / 16;
   c.KC = 0;
   for (int kc = 4; kc >= 1; kc >>= 1) {
     if (chunks % kc) continue;
-    int stage = kc * (2 * c.P_alloc * 16 + ntyx * 2 * c.Nc * 16);
+    int stage = kc * (2 * c.P_alloc * 16 + c.ntyx * 2 * c.Nc * 16);
     int st = avail / stage;
     if (st >= 3 || (kc == 1 && st >= 2)) {
       c.KC = kc;
@@ -128,9 +182,9 @@ static bool plan_umma(const ConvArgs& a, UmmaCfg& c) {
   if (!c.KC) return false;
   c.G = chunks / c.KC;
   c.a_stage_bytes = c.KC * 2 * c.P_alloc * 16;
-  c.b_stage_bytes = c.KC * ntyx * 2 * c.Nc * 16;
+  c.b_stage_bytes = c.KC * c.ntyx * 2 * c.Nc * 16;
   c.smem_bytes = c.stages * (c.a_stage_bytes + c.b_stage_bytes) + misc;
-  c.wp_magic = (unsigned)((0x100000000ull + (unsigned)c.Wp - 1) / (unsigned)c.Wp);
+  c.pitch_magic = (unsigned)((0x100000000ull + (unsigned)c.pitch - 1) / (unsigned)c.pitch);
   if ((c.P_alloc * 16 >> 4) > 0x3FFF || (c.Nc * 16 >> 4) > 0x3FFF) return false;
   c.ok = 1;
   return true;
@@ -202,9 +256,8 @@ struct UnitIdx {
 };
 __device__ __forceinline__ UnitIdx decode_unit(const UmmaArgs& p, int u) {
   UnitIdx r;
-  const int D = p.a.out_d[0];
-  r.z = u % D;
-  u /= D;
+  r.z = u % p.c.Dz;
+  u /= p.c.Dz;
   r.yb = u % p.c.n_yblocks;
   u /= p.c.n_yblocks;
   r.nc = u % p.c.n_chunks;
@@ -223,15 +276,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   uint64_t* tfull_bar = empty_bar + 4;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* xs = reinterpret_cast<float*>(tmem_slot + 4);
+  uint32_t* tile_tab = tmem_slot + 4;                       // [64] tile base positions
+  float* xs = reinterpret_cast<float*>(tile_tab + 64);
   float* xh = xs + a.cin;
   float* xl = xh + a.cin;
   float* stat_s = xl + a.cin;   // [2][Nc]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int D = a.in_d[0], H = a.in_d[1], W = a.in_d[2];
-  const int ntyx = c.nky * c.nkx;
+  const int Din = a.in_d[0], Hin = a.in_d[1], Win = a.in_d[2];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
@@ -245,6 +298,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 2 * c.Nc; i += blockDim.x) stat_s[i] = 0.f;
+  for (int i = threadIdx.x; i < c.T; i += blockDim.x) tile_tab[i] = (uint32_t)tile_base_of(c, i);
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -259,8 +313,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     // =========================== PRODUCERS ===========================
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
-    const int q = tid % Q;
-    const int items = c.P_fill * Q;
+    const int qshift = (Q == 2) ? 1 : (Q == 4 ? 2 : 3);
+    const int q = tid & (Q - 1);
+    const int items = c.P_fill << qshift;
     int stage = 0;
     uint32_t phase = 0;
     int cur_b = -1;
@@ -281,9 +336,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
       }
       const int y0 = ui.yb * c.TY;
       for (int kz = 0; kz < c.nkz; ++kz) {
-        const int z_in = ui.z + kz - c.pz;
-        if (z_in < 0 || z_in >= D) continue;
-        const __half* plane = a.src + ((size_t)ui.b * D + z_in) * H * W * a.src_cs;
+        const int z_in = ui.z * c.sz + kz - c.pz;
+        if (z_in < 0 || z_in >= Din) continue;
+        const __half* plane = a.src + ((size_t)ui.b * Din + z_in) * Hin * Win * a.src_cs;
         for (int g = 0; g < c.G; ++g) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_s = ring + (size_t)stage * stage_bytes;
@@ -302,44 +357,48 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
             sh[e] = xh[ch0 + e];
             sl[e] = xl[ch0 + e];
           }
-          uint8_t* a_q = a_s + (size_t)q * c.P_alloc * 16;
-          constexpr int U = 4;
-          for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
-            uint4 raw[U];
-            int pos[U];
-            bool ok[U];
+          for (int phy = 0; phy < c.nph_y; ++phy) {
+            for (int phx = 0; phx < c.nph_x; ++phx) {
+              uint8_t* a_q = a_s + ((size_t)q * c.P_alloc + (size_t)(phy * c.nph_x + phx) * c.P_plane) * 16;
+              constexpr int U = 4;
+              for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
+                uint4 raw[U];
+                int pos[U];
+                bool ok[U];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              const int j = j0 + k * kProducerThreads;
-              const int pp = j / Q;
-              pos[k] = (j < items) ? pp : -1;
-              const int r = (int)__umulhi((unsigned)pp, c.wp_magic);
-              const int xp = pp - r * c.Wp;
-              const int y_in = y0 - c.py + r;
-              const int x_in = xp - c.px;
-              ok[k] = (j < items) && y_in >= 0 && y_in < H && x_in >= 0 && x_in < W;
-              raw[k] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(plane + ((size_t)y_in * W + x_in) * a.src_cs + ch0));
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-              if (pos[k] < 0) continue;
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[k]) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k]);
-                __half2 r2[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __half22float2(h2[e]);
-                  float v0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                  float v1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                  v0 = fmaxf(v0, v0 * sl[2 * e]);
-                  v1 = fmaxf(v1, v1 * sl[2 * e + 1]);
-                  r2[e] = __floats2half2_rn(v0, v1);
+                for (int k = 0; k < U; ++k) {
+                  const int j = j0 + k * kProducerThreads;
+                  const int pp = j >> qshift;
+                  pos[k] = (j < items) ? pp : -1;
+                  const int r = (int)__umulhi((unsigned)pp, c.pitch_magic);
+                  const int xp = pp - r * c.pitch;
+                  const int y_in = c.sy * (y0 + r - c.lead_y) + phy;
+                  const int x_in = c.sx * (xp - c.lead_x) + phx;
+                  ok[k] = (j < items) && y_in >= 0 && y_in < Hin && x_in >= 0 && x_in < Win;
+                  raw[k] = make_uint4(0u, 0u, 0u, 0u);
+                  if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(plane + ((size_t)y_in * Win + x_in) * a.src_cs + ch0));
                 }
-                o = *reinterpret_cast<uint4*>(r2);
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                  if (pos[k] < 0) continue;
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (ok[k]) {
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k]);
+                    __half2 r2[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      float2 f = __half22float2(h2[e]);
+                      float v0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                      float v1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                      v0 = fmaxf(v0, v0 * sl[2 * e]);
+                      v1 = fmaxf(v1, v1 * sl[2 * e + 1]);
+                      r2[e] = __floats2half2_rn(v0, v1);
+                    }
+                    o = *reinterpret_cast<uint4*>(r2);
+                  }
+                  *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
+                }
               }
-              *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -350,68 +409,84 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     }
   } else if (warp == 8) {
     // =========================== MMA ISSUER ===========================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(c.Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)c.P_alloc * 16, b_lbo = (uint32_t)c.Nc * 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      int buf = 0;
-      uint32_t tphase[2] = {0, 0};
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const UnitIdx ui = decode_unit(p, u);
-        mbar_wait(&tempty_bar[buf], tphase[buf] ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)buf * buf_cols;
-        bool first = true;
-        for (int kz = 0; kz < c.nkz; ++kz) {
-          const int z_in = ui.z + kz - c.pz;
-          if (z_in < 0 || z_in >= D) continue;
-          for (int g = 0; g < c.G; ++g) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(ring + (size_t)stage * stage_bytes);
-            const uint32_t b_base = a_base + (uint32_t)c.a_stage_bytes;
-            for (int kc = 0; kc < c.KC; ++kc) {
-              for (int t = 0; t < ntyx; ++t) {
-                const int ky = t / c.nkx, kx = t - ky * c.nkx;
-                const uint64_t db = make_desc(b_base + (uint32_t)((kc * ntyx + t) * 2) * b_lbo, b_lbo, 128);
-                const uint32_t a_off = a_base + (uint32_t)(kc * 2) * a_lbo + (uint32_t)(ky * c.Wp + kx) * 16;
-                const uint32_t accum = (first && kc == 0 && t == 0) ? 0u : 1u;
-                for (int i = 0; i < c.T; ++i) {
-                  const uint64_t da = make_desc(a_off + (uint32_t)tile_base_of(c, i) * 16, a_lbo, 128);
-                  umma_f16(d_base + (uint32_t)(i * c.Nc), da, db, idesc, accum);
-                }
+    // The whole warp runs the (uniform) control flow; lane 0 issues.  Per MMA: one shared-memory read of
+    // the tile base, one 64-bit add on the A descriptor, one add on the TMEM column.
+    const bool leader = lane == 0;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(c.Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_lbo = (uint32_t)c.P_alloc * 16, b_lbo = (uint32_t)c.Nc * 16;
+    const uint64_t a_desc0 = make_desc(0, a_lbo, 128);
+    const uint64_t b_desc0 = make_desc(0, b_lbo, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t tphase0 = 0, tphase1 = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const UnitIdx ui = decode_unit(p, u);
+      mbar_wait(buf ? &tempty_bar[1] : &tempty_bar[0], (buf ? tphase1 : tphase0) ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)buf * buf_cols;
+      bool first = true;
+      for (int kz = 0; kz < c.nkz; ++kz) {
+        const int z_in = ui.z * c.sz + kz - c.pz;
+        if (z_in < 0 || z_in >= Din) continue;
+        for (int g = 0; g < c.G; ++g) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + (size_t)stage * stage_bytes);
+          const uint32_t b_base = a_base + (uint32_t)c.a_stage_bytes;
+          for (int kc = 0; kc < c.KC; ++kc) {
+            for (int t = 0; t < c.ntyx; ++t) {
+              const uint64_t db = b_desc0 + (uint64_t)((b_base + (uint32_t)((kc * c.ntyx + t) * 2) * b_lbo) >> 4);
+              const uint64_t da0 = a_desc0 + (uint64_t)((a_base + (uint32_t)(kc * 2) * a_lbo + (uint32_t)c.tap_aoff[t] * 16) >> 4);
+              const uint32_t accum = (first && kc == 0 && t == 0) ? 0u : 1u;
+              uint32_t d = d_base;
+#pragma unroll 4
+              for (int i = 0; i < c.T; ++i) {
+                const uint64_t da = da0 + (uint64_t)tile_tab[i];
+                if (leader) umma_f16(d, da, db, idesc, accum);
+                d += (uint32_t)c.Nc;
               }
             }
-            umma_commit(&empty_bar[stage]);
-            first = false;
-            if (++stage == c.stages) { stage = 0; phase ^= 1; }
           }
+          if (leader) umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          first = false;
+          if (++stage == c.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);
-        tphase[buf] ^= 1;
-        if (c.tmem_bufs == 2) buf ^= 1;
       }
+      if (leader) umma_commit(buf ? &tfull_bar[1] : &tfull_bar[0]);
+      __syncwarp();
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+      if (c.tmem_bufs == 2) buf ^= 1;
     }
-    __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 4 * 32;         // 0..127
-    const int c0 = c.py * c.Wp + c.px;
     int buf = 0;
-    uint32_t tphase[2] = {0, 0};
+    uint32_t tphase0 = 0, tphase1 = 0;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
+    const int Dout = a.out_d[0], Hout = a.out_d[1], Wout = a.out_d[2];
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const UnitIdx ui = decode_unit(p, u);
       const int y0 = ui.yb * c.TY;
-      mbar_wait(&tfull_bar[buf], tphase[buf]);
-      tphase[buf] ^= 1;
+      mbar_wait(buf ? &tfull_bar[1] : &tfull_bar[0], buf ? tphase1 : tphase0);
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(wq * 32) << 16);
-      __half* out_plane = a.dst + ((size_t)ui.b * D + ui.z) * H * W * a.dst_cs;
+      __half* out_b = a.dst + (size_t)ui.b * Dout * Hout * Wout * a.dst_cs;
       for (int n0 = 0; n0 < c.Nc; n0 += 16) {
-        const int co0 = ui.nc * c.Nc + n0;
+        const int v0 = ui.nc * c.Nc + n0;          // first (virtual) output channel of this 16-group
+        int co0 = v0, oz = ui.z, oy_off = 0, ox_off = 0, ys = 1, xsn = 1;
+        if (c.transposed) {
+          const int tap = v0 / a.cout_pad;
+          co0 = v0 - tap * a.cout_pad;
+          const int ddx = tap % a.s[2];
+          const int ddy = (tap / a.s[2]) % a.s[1];
+          const int ddz = tap / (a.s[2] * a.s[1]);
+          oz = ui.z * a.s[0] + ddz;
+          oy_off = ddy; ox_off = ddx; ys = a.s[1]; xsn = a.s[2];
+        }
         float bias[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) bias[j] = (a.bias && co0 + j < a.cout) ? __ldg(a.bias + co0 + j) : 0.f;
@@ -419,13 +494,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
         const bool full16 = co0 + 16 <= a.cout;
+        __half* out_plane = out_b + (size_t)oz * Hout * Wout * a.dst_cs;
         for (int i = 0; i < c.T; ++i) {
-          const int pc = tile_base_of(c, i) + c0 + wq * 32 + lane;
-          const int r = (int)__umulhi((unsigned)pc, c.wp_magic);
-          const int xp = pc - r * c.Wp;
-          const int yo = r - c.py, xo = xp - c.px;
+          const int pos = (int)tile_tab[i] + wq * 32 + lane;
+          const int yo = (int)__umulhi((unsigned)pos, c.pitch_magic);
+          const int xo = pos - yo * c.pitch;
           const int y = y0 + yo;
-          const bool valid = xo >= 0 && xo < W && yo < c.TY && y < H;
+          const bool valid = xo < c.Wo && yo < c.TY && y < c.Ho;
           uint32_t acc[16];
           tmem_ld16(d_base + (uint32_t)(i * c.Nc + n0), acc);
           if (valid) {
@@ -437,7 +512,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
               s1[j] += f;
               s2[j] = fmaf(f, f, s2[j]);
             }
-            __half* q = out_plane + ((size_t)y * W + xo) * a.dst_cs + co0;
+            __half* q = out_plane + ((size_t)(y * ys + oy_off) * Wout + (xo * xsn + ox_off)) * a.dst_cs + co0;
             if (vec_store && full16) {
               reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
               reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
@@ -467,7 +542,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      mbar_arrive(buf ? &tempty_bar[1] : &tempty_bar[0]);
       if (c.tmem_bufs == 2) buf ^= 1;
       if (a.dst_stats) {
         named_bar_sync(2, kEpilogueThreads);
@@ -494,25 +569,29 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 //   [n-chunk][kz][group g][chunk kc][tap (ky,kx)][8-channel half][n < Nc][8 halves]
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_umma_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout,
-                                         UmmaCfg c) {
-  const int ntyx = c.nky * c.nkx;
-  const size_t total = (size_t)c.n_chunks * c.nkz * c.G * c.KC * ntyx * 2 * c.Nc * 8;
+                                         int cout_pad, int ntaps, int nky, int nkx, UmmaCfg c) {
+  const size_t total = (size_t)c.n_chunks * c.nkz * c.G * c.KC * c.ntyx * 2 * c.Nc * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int e = (int)(r % 8); r /= 8;
     const int n = (int)(r % c.Nc); r /= c.Nc;
     const int h = (int)(r % 2); r /= 2;
-    const int t = (int)(r % ntyx); r /= ntyx;
+    const int t = (int)(r % c.ntyx); r /= c.ntyx;
     const int kc = (int)(r % c.KC); r /= c.KC;
     const int g = (int)(r % c.G); r /= c.G;
     const int kz = (int)(r % c.nkz); r /= c.nkz;
     const int nc = (int)r;
-    const int co = nc * c.Nc + n;
+    const int v = nc * c.Nc + n;                      // (virtual) output channel
     const int ci = (g * c.KC + kc) * 16 + h * 8 + e;
-    const int ky = t / c.nkx, kx = t % c.nkx;
-    float v = 0.f;
-    if (co < cout) v = w[((((size_t)co * cin + ci) * c.nkz + kz) * c.nky + ky) * c.nkx + kx];
-    out[i] = __float2half_rn(v);
+    float val = 0.f;
+    if (c.transposed) {
+      const int tap = v / cout_pad, co = v - tap * cout_pad;    // weight [cin][cout][taps]
+      if (co < cout) val = w[((size_t)ci * cout + co) * ntaps + tap];
+    } else {
+      const int ky = t / nkx, kx = t % nkx;                     // weight [cout][cin][kz][ky][kx]
+      if (v < cout) val = w[((((size_t)v * cin + ci) * c.nkz + kz) * nky + ky) * nkx + kx];
+    }
+    out[i] = __float2half_rn(val);
   }
 }
 
@@ -522,7 +601,8 @@ bool umma_supported(const ConvArgs& a) {
 }
 
 size_t umma_packed_weight_bytes(int cin, int cout, int ntaps, int transposed) {
-  if (transposed || cin % 16 != 0) return 0;
+  (void)transposed;
+  if (cin % 16 != 0) return 0;
   const int cout_pad = (cout + 15) / 16 * 16;
   return (size_t)ntaps * cin * cout_pad * sizeof(__half);
 }
@@ -533,7 +613,8 @@ int launch_pack_weights_umma(const float* w_dev, void* out, const ConvArgs& a, c
   const size_t total = (size_t)a.ntaps * a.cin * a.cout_pad;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  pack_weights_umma_kernel<<<blocks, 256, 0, s>>>(w_dev, (__half*)out, a.cin, a.cout, c);
+  pack_weights_umma_kernel<<<blocks, 256, 0, s>>>(w_dev, (__half*)out, a.cin, a.cout, a.cout_pad, a.ntaps,
+                                                  a.transposed ? 1 : a.k[1], a.transposed ? 1 : a.k[2], c);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }
@@ -545,7 +626,7 @@ int launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     set_error("conv_umma: unsupported shape");
     return FNNU_E_UNSUPPORTED;
   }
-  p.n_units = a.batch * p.c.n_chunks * p.c.n_yblocks * a.out_d[0];
+  p.n_units = a.batch * p.c.n_chunks * p.c.n_yblocks * p.c.Dz;
   static bool attr_set = false;
   if (!attr_set) {
     FNNU_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));

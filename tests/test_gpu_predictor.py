@@ -71,8 +71,14 @@ def test_sliding_window_matches_oracle(tmp_path, name, vol):
     got = p.predict_sliding_window_return_logits(x)
     assert got.dtype == torch.float16 and tuple(got.shape) == (spec['heads'], *vol) and got.device.type == 'cuda'
     _compare(got, _oracle(net, x.half().float(), spec['patch']), spec['heads'])
+    # fused argmax == argmax of the logits of the SAME run (bit-exact); a second run may differ in a few near-ties
+    # because the fp64 InstanceNorm sums are accumulated with atomics in arbitrary order
+    data, revert = p._pad(x)
+    lg, lb = p._internal_predict_sliding_window_return_logits(data, p._internal_get_sliding_window_slicers(data.shape[1:]),
+                                                              True, return_labels=True)
+    assert np.array_equal(lb.cpu().numpy(), OP.logits_to_segmentation(lg).astype(np.uint8))
     labels = p.predict_sliding_window_return_segmentation(x)
-    assert np.array_equal(labels.cpu().numpy(), OP.logits_to_segmentation(got).astype(np.uint8))
+    assert float((labels.cpu().numpy() == OP.logits_to_segmentation(got)).mean()) >= 0.999
     assert p.last_launches > 0
 
 
