@@ -229,6 +229,248 @@ int launch_conv_direct(const ConvArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// First layer: Cin <= 4 (1 CT channel, 4 MRI channels), stride 1, kernel 1|3 per axis, Cout <= 64.
+// K = taps * Cin is too thin for the tensor cores (0.8 % of the network's FLOPs), so this is a
+// CUDA-core kernel: weights broadcast from shared memory, each thread owns 4 consecutive x voxels and
+// 16 output channels, each loaded input row segment is reused by the 3 kx taps.
+// ------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128) conv_small_cin_kernel(ConvArgs a) {
+  extern __shared__ float smem[];
+  float* w_s = smem;                                    // [ntaps][CIN][16]
+  float* red = w_s + a.ntaps * CIN * 16;                // [4][32]
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < a.ntaps * CIN * 16; i += 128) {
+    int o = i & 15, rest = i >> 4;                      // rest = tap * CIN + ci
+    w_s[i] = __ldg(a.w + (size_t)rest * a.cout_pad + co0 + o);
+  }
+  __syncthreads();
+  float xs[CIN], xh[CIN], xl[CIN];     // pending transform of the source (identity for the network input)
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) {
+    const ChanMeta m = a.src_meta[c];
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, m, a.src_inv_count, xs[c], xh[c]);
+    xl[c] = m.eps < 0.f ? 1.f : m.slope;
+  }
+  const int D0 = a.out_d[0], D1 = a.out_d[1], D2 = a.out_d[2];
+  const int gpr = (D2 + 3) / 4;
+  const long long n_groups = (long long)D0 * D1 * gpr;
+  const long long gidx = (long long)blockIdx.x * 128 + threadIdx.x;
+  const bool active = gidx < n_groups;
+  float acc[4][16];
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[v][o] = 0.f;
+  int x0 = 0, y = 0, z = 0;
+  if (active) {
+    x0 = (int)(gidx % gpr) * 4;
+    y = (int)((gidx / gpr) % D1);
+    z = (int)(gidx / ((long long)gpr * D1));
+    const __half* src_b = a.src + (size_t)b * D0 * D1 * D2 * a.src_cs;
+    const int nx = a.k[2] + 3;                           // input columns needed for 4 outputs
+    for (int kz = 0; kz < a.k[0]; ++kz) {
+      const int iz = z + kz - a.pad[0];
+      if (iz < 0 || iz >= D0) continue;
+      for (int ky = 0; ky < a.k[1]; ++ky) {
+        const int iy = y + ky - a.pad[1];
+        if (iy < 0 || iy >= D1) continue;
+        const __half* row = src_b + ((size_t)iz * D1 + iy) * D2 * a.src_cs;
+        float in[6][CIN];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int ix = x0 + j - a.pad[2];
+          const bool ok = j < nx && ix >= 0 && ix < D2;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c)
+            in[j][c] = ok ? lrelu(fmaf(__half2float(__ldg(row + (size_t)ix * a.src_cs + c)), xs[c], xh[c]), xl[c]) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          if (kx >= a.k[2]) break;
+          const int tap = (kz * a.k[1] + ky) * a.k[2] + kx;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float4* wt = reinterpret_cast<const float4*>(w_s + ((size_t)tap * CIN + c) * 16);
+            float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+            float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+              for (int o = 0; o < 16; ++o) acc[v][o] = fmaf(in[v + kx][c], wv[o], acc[v][o]);
+          }
+        }
+      }
+    }
+  }
+  float s1[16], s2[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) s1[o] = s2[o] = 0.f;
+  if (active) {
+    __half* dst_b = a.dst + (size_t)b * D0 * D1 * D2 * a.dst_cs;
+    const bool vec_out = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && (co0 + 16 <= a.cout);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (x0 + v >= D2) continue;
+      __half* q = dst_b + (((size_t)z * D1 + y) * D2 + x0 + v) * a.dst_cs + co0;
+      __half hv[16];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        float val = acc[v][o] + ((a.bias && co0 + o < a.cout) ? __ldg(a.bias + co0 + o) : 0.f);
+        hv[o] = __float2half_rn(val);
+        float r = __half2float(hv[o]);
+        s1[o] += r;
+        s2[o] += r * r;
+      }
+      if (vec_out) {
+        reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
+        reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+          if (co0 + o < a.cout) q[o] = hv[o];
+      }
+    }
+  }
+  if (a.dst_stats) {
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        s1[o] += __shfl_xor_sync(0xffffffffu, s1[o], off);
+        s2[o] += __shfl_xor_sync(0xffffffffu, s2[o], off);
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        red[warp * 32 + o] = s1[o];
+        red[warp * 32 + 16 + o] = s2[o];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int o = threadIdx.x & 15, which = threadIdx.x >> 4;
+      double tot = 0.0;
+      for (int w = 0; w < 4; ++w) tot += (double)red[w * 32 + which * 16 + o];
+      if (co0 + o < a.cout) atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + co0 + o) * 2 + which, tot);
+    }
+  }
+}
+
+static bool small_cin_ok(const ConvArgs& a) {
+  if (a.transposed || a.cin > 4) return false;
+  for (int i = 0; i < 3; ++i)
+    if (a.s[i] != 1 || (a.k[i] != 1 && a.k[i] != 3)) return false;
+  return a.cout_pad <= 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segmentation head: 1x1x1 conv to <= 8 heads.  HBM-bound (reads Cin fp16 per voxel, writes the logits):
+// one thread per voxel, 128-bit loads, source transform applied on the fly, no InstanceNorm sums.
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_pointwise_head_kernel(ConvArgs a) {
+  extern __shared__ float smem[];
+  float* w_s = smem;                 // [COUT][cin]
+  float* xs = w_s + COUT * a.cin;    // scale, shift, slope [cin] per sample (recomputed when b changes)
+  float* xh = xs + a.cin;
+  float* xl = xh + a.cin;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < COUT * a.cin; i += 256) {
+    int co = i / a.cin, ci = i - co * a.cin;
+    w_s[i] = co < a.cout ? __ldg(a.w + (size_t)ci * a.cout_pad + co) : 0.f;     // packed [tap=0][cin][cout_pad]
+  }
+  for (int c = threadIdx.x; c < a.cin; c += 256) {
+    float sc, sh;
+    const ChanMeta m = a.src_meta[c];
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, m, a.src_inv_count, sc, sh);
+    xs[c] = sc;
+    xh[c] = sh;
+    xl[c] = m.eps < 0.f ? 1.f : m.slope;
+  }
+  __syncthreads();
+  const size_t nv = (size_t)a.in_d[0] * a.in_d[1] * a.in_d[2];
+  const __half* src_b = a.src + (size_t)b * nv * a.src_cs;
+  __half* dst_b = a.dst + (size_t)b * nv * a.dst_cs;
+  float bias[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) bias[o] = (a.bias && o < a.cout) ? __ldg(a.bias + o) : 0.f;
+  for (size_t v = (size_t)blockIdx.x * 256 + threadIdx.x; v < nv; v += (size_t)gridDim.x * 256) {
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = bias[o];
+    const uint4* p = reinterpret_cast<const uint4*>(src_b + v * a.src_cs);
+    for (int c8 = 0; c8 < a.cin; c8 += 8) {
+      const uint4 raw = __ldg(p + (c8 >> 3));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        const int c = c8 + 2 * e;
+        float v0 = fmaf(f.x, xs[c], xh[c]);
+        float v1 = fmaf(f.y, xs[c + 1], xh[c + 1]);
+        v0 = fmaxf(v0, v0 * xl[c]);
+        v1 = fmaxf(v1, v1 * xl[c + 1]);
+        // the tensor-core layers feed fp16-rounded activations to the MMA; round here too so that all
+        // back ends see the same operand values
+        v0 = __half2float(__float2half_rn(v0));
+        v1 = __half2float(__float2half_rn(v1));
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v0, w_s[o * a.cin + c], fmaf(v1, w_s[o * a.cin + c + 1], acc[o]));
+      }
+    }
+    __half* q = dst_b + v * a.dst_cs;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o)
+      if (o < a.cout) q[o] = __float2half_rn(acc[o]);
+  }
+}
+
+static bool pointwise_head_ok(const ConvArgs& a) {
+  if (a.transposed || a.dst_stats) return false;
+  if (a.k[0] != 1 || a.k[1] != 1 || a.k[2] != 1 || a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
+  return a.cout <= 8 && a.cin % 8 == 0 && a.cin <= 1024 && a.src_cs % 8 == 0 && ((uintptr_t)a.src % 16) == 0;
+}
+
+bool direct_specialised(const ConvArgs& a) { return small_cin_ok(a) || pointwise_head_ok(a); }
+bool prefer_cuda_cores(const ConvArgs& a) { return pointwise_head_ok(a); }
+
+int launch_conv_specialised(const ConvArgs& a, cudaStream_t s) {
+  if (pointwise_head_ok(a)) {
+    const size_t nv = (size_t)a.in_d[0] * a.in_d[1] * a.in_d[2];
+    int blocks = (int)((nv + 255) / 256);
+    int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)a.batch);
+    const int co = a.cout <= 2 ? 2 : (a.cout <= 4 ? 4 : 8);
+    size_t smem = (size_t)(co * a.cin + 3 * a.cin) * sizeof(float);
+    if (co == 2) conv_pointwise_head_kernel<2><<<grid, 256, smem, s>>>(a);
+    else if (co == 4) conv_pointwise_head_kernel<4><<<grid, 256, smem, s>>>(a);
+    else conv_pointwise_head_kernel<8><<<grid, 256, smem, s>>>(a);
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
+  if (small_cin_ok(a)) {
+    long long groups = (long long)a.out_d[0] * a.out_d[1] * ((a.out_d[2] + 3) / 4);
+    dim3 grid((unsigned)((groups + 127) / 128), (unsigned)(a.cout_pad / 16), (unsigned)a.batch);
+    size_t smem = (size_t)(a.ntaps * a.cin * 16 + 4 * 32) * sizeof(float);
+    switch (a.cin) {
+      case 1: conv_small_cin_kernel<1><<<grid, 128, smem, s>>>(a); break;
+      case 2: conv_small_cin_kernel<2><<<grid, 128, smem, s>>>(a); break;
+      case 3: conv_small_cin_kernel<3><<<grid, 128, smem, s>>>(a); break;
+      default: conv_small_cin_kernel<4><<<grid, 128, smem, s>>>(a); break;
+    }
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
+  set_error("conv_specialised: unsupported shape");
+  return FNNU_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: PyTorch layouts -> [tap][cin][cout_pad] fp32
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_direct_kernel(const float* __restrict__ w, float* __restrict__ out, int cin, int cout,

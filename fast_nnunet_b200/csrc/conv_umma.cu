@@ -11,14 +11,14 @@
 // Shared-memory operand layout (no swizzle, K-major canonical layout of the UMMA descriptor):
 //   A stage : [8-channel group q][position p][8 halves]   -> row pitch 16 B, SBO = 128 B, LBO = plane
 //   B stage : [chunk][tap][8-channel group][cout n][8 halves]
-// A is written by 4 producer warps that read the RAW fp16 output of the previous layer from HBM/L2 and
+// A is written by 8 producer warps that read the RAW fp16 output of the previous layer from HBM/L2 and
 // apply its InstanceNorm affine + LeakyReLU on the way (the fused "normalise on load"); B (weights,
 // pre-packed per stage) arrives by one cp.async.bulk (TMA engine) per stage.  One thread issues the
 // MMAs; 4 epilogue warps drain TMEM (tcgen05.ld), add the bias, round to fp16, store channels-last and
 // accumulate the InstanceNorm sums of the rounded values (fp32 partials -> fp64 atomics).
 //
-// Warp roles (288 threads): warps 0-3 producers, warps 4-7 epilogue (TMEM lane quarter = warp % 4),
-// warp 8 MMA issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
+// Warp roles (416 threads): warps 0-7 producers, warps 8-11 epilogue (TMEM lane quarter = warp % 4),
+// warp 12 MMA issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
 // and MMA; TMEM accumulator buffers (full/empty mbarriers) between MMA and epilogue.
 //
 // Strided convolutions keep the same structure through a phase decomposition: with stride s the tap k
@@ -63,9 +63,11 @@ struct UmmaArgs {
   int n_units;
 };
 
-constexpr int kProducerThreads = 128;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
-constexpr int kThreadsUmma = 288;
+constexpr int kMmaWarp = kProducerWarps + 4;
+constexpr int kThreadsUmma = (kMmaWarp + 1) * 32;
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline int tile_base_of(const UmmaCfg& c, int i) {
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   }
   for (int i = threadIdx.x; i < 2 * c.Nc; i += blockDim.x) stat_s[i] = 0.f;
   for (int i = threadIdx.x; i < c.T; i += blockDim.x) tile_tab[i] = (uint32_t)tile_base_of(c, i);
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(c.T * c.Nc);
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // =========================== PRODUCERS ===========================
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           for (int phy = 0; phy < c.nph_y; ++phy) {
             for (int phx = 0; phx < c.nph_x; ++phx) {
               uint8_t* a_q = a_s + ((size_t)q * c.P_alloc + (size_t)(phy * c.nph_x + phx) * c.P_plane) * 16;
-              constexpr int U = 4;
+              constexpr int U = 8;
               for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
                 uint4 raw[U];
                 int pos[U];
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // The whole warp runs the (uniform) control flow; lane 0 issues.  Per MMA: one shared-memory read of
     // the tile base, one 64-bit add on the A descriptor, one add on the TMEM column.
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   } else {
     // =========================== EPILOGUE ===========================
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 4 * 32;         // 0..127
+    const int et = threadIdx.x - kProducerThreads;   // 0..127
     int buf = 0;
     uint32_t tphase0 = 0, tphase1 = 0;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }

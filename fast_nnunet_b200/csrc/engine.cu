@@ -387,9 +387,11 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
     int rc = FNNU_OK;
     if (op.kind == FNNU_OP_CONV || op.kind == FNNU_OP_TCONV) {
       op.conv.batch = batch;
-      if (op.umma_ok && e->backend == 0) {
+      if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
         rc = launch_conv_umma(op.conv, s);
         ++umma;
+      } else if (e->backend == 0 && direct_specialised(op.conv)) {
+        rc = launch_conv_specialised(op.conv, s);
       } else {
         rc = launch_conv_direct(op.conv, s);
       }

@@ -50,6 +50,10 @@ struct EltArgs {
 int num_sms();
 
 int launch_conv_direct(const ConvArgs& a, cudaStream_t s);
+// CUDA-core specialisations: first layer (Cin <= 4) and the 1x1x1 segmentation head (<= 8 heads)
+bool direct_specialised(const ConvArgs& a);
+bool prefer_cuda_cores(const ConvArgs& a);     // true where the specialised kernel beats the tensor-core path
+int launch_conv_specialised(const ConvArgs& a, cudaStream_t s);
 int launch_pack_weights_direct(const float* w_dev, float* out, int cin, int cout, int cout_pad, int ntaps,
                                int transposed, cudaStream_t s);
 int launch_add_act(const EltArgs& a, cudaStream_t s);
