@@ -1,0 +1,436 @@
+// Row-streaming tcgen05 convolution for the thin, full-resolution layers (Cout <= 32, W <= 128 ...):
+// the layers that hold most of a nnU-Net's FLOPs (48 % at 128^3 with Cout = 16).
+//
+// Why a second kernel.  With A read from shared memory a 128 x N x 16 tcgen05.mma costs ~64 cycles of
+// operand fetch (4 KB of A at 64 B/clk, measured: tc pipe busy 53 %, tensor math 6 % on the generic
+// kernel) no matter how small N is; its math takes only N/2 cycles.  A 3x3x3 conv with Cout = 16 issued
+// as 27 taps x (N = 16) is therefore operand-fetch bound at <= 12 % of the tensor peak.  Here the ky taps
+// are FOLDED INTO N:   D'[row r][x, (ky, co)] = sum_{kz, kx, ci} X[z + kz - 1, r, x + kx - 1, ci] * W[kz, ky, kx][ci, co]
+// is one accumulator tile per INPUT row r (N = 3 * Cout, 9 MMAs per 16 input channels instead of 27), and
+//   out[y][x, co] = D'[y - 1][x, (2, co)] + D'[y][x, (1, co)] + D'[y + 1][x, (0, co)]
+// is a sum of three accumulator tiles AT THE SAME LANE, done by the epilogue while it drains TMEM — no
+// cross-lane traffic.  Because an input row now feeds exactly one accumulator tile, the kernel streams:
+//   producers (4 groups x 2 warps): one smem stage = one input row x 3 z-planes x Cin, normalise-on-load
+//   MMA warp: 9 * Cin/16 MMAs per stage into a ring of TMEM tile slots, commit per row
+//   epilogue (4 warps): output row y as soon as tile y+1 is complete; frees tile y-1
+// Weights (all 27 taps) stay resident in shared memory for the whole kernel (<= 64 KB).
+#include "common.cuh"
+#include "ops.cuh"
+#include "umma_ptx.cuh"
+
+namespace fnnu {
+
+struct RowsCfg {
+  int ok;
+  int nkz, nkx, pz, px;
+  int Nf;                 // 3 * cout_pad: N of every MMA
+  int chunks;             // Cin / 16
+  int Q;                  // Cin / 8 (8-channel groups)
+  int W, H, D;
+  int P_row;              // positions allocated per (kz, group) row in smem
+  int stage_bytes, stages;
+  int w_bytes;
+  int slots;              // TMEM tile slots (Nf columns each)
+  int n_yseg, seg_rows;
+  int smem_bytes;
+};
+
+struct RowsArgs {
+  ConvArgs a;
+  RowsCfg c;
+  int n_units;
+};
+
+constexpr int kRowsProducerGroups = 4;
+constexpr int kRowsGroupThreads = 64;
+constexpr int kRowsProducerThreads = kRowsProducerGroups * kRowsGroupThreads;   // warps 0-7
+constexpr int kRowsEpiWarp0 = 8;                                                // warps 8-11
+constexpr int kRowsMmaWarp = 12;
+constexpr int kRowsThreads = 13 * 32;
+constexpr int kRowsMaxStages = 16;
+constexpr int kRowsMaxSlots = 10;
+constexpr int kRowsSmemLimit = 227 * 1024;
+
+static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
+  memset(&c, 0, sizeof(c));
+  if (a.transposed) return false;
+  if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
+  if (a.k[1] != 3) return false;                         // the folded axis
+  if (a.cin % 16 != 0 || a.cin < 16 || a.cin > 64) return false;
+  if (a.cout_pad != 16 && a.cout_pad != 32) return false;   // per-thread InstanceNorm partials live in registers
+  if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
+  c.D = a.in_d[0]; c.H = a.in_d[1]; c.W = a.in_d[2];
+  if (c.W > 128 || c.W < 64) return false;               // one M-tile per row; below 64 the generic kernel packs better
+  c.nkz = a.k[0]; c.nkx = a.k[2]; c.pz = a.pad[0]; c.px = a.pad[2];
+  c.Nf = 3 * a.cout_pad;
+  c.chunks = a.cin / 16;
+  c.Q = a.cin / 8;
+  // positions read by an MMA tile: [kx, kx + 128); keep the row stride = 4 (mod 8) positions for the banks
+  int need = 128 + (c.nkx - 1);
+  if (need < c.W + 2 * c.px) need = c.W + 2 * c.px;
+  c.P_row = (need + 7) / 8 * 8 + 4;
+  c.stage_bytes = c.nkz * c.Q * c.P_row * 16;
+  c.w_bytes = c.nkz * c.nkx * c.chunks * 2 * c.Nf * 16;
+  if (c.w_bytes > 80 * 1024) return false;
+  const int misc = 1024 + 3 * a.cin * 4 + 1024;
+  int st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
+  if (st < 4) return false;
+  c.stages = st > kRowsMaxStages ? kRowsMaxStages : st;
+  c.slots = 512 / c.Nf;
+  if (c.slots > kRowsMaxSlots) c.slots = kRowsMaxSlots;
+  if (c.slots < 4) return false;
+  c.smem_bytes = c.w_bytes + c.stages * c.stage_bytes + misc;
+  // units: (sample, z, y segment).  Whole columns unless that leaves SMs idle.
+  c.n_yseg = 1;
+  while ((long long)a.batch * c.D * c.n_yseg < 3LL * num_sms() && c.H / (c.n_yseg * 2) >= 8) c.n_yseg *= 2;
+  c.seg_rows = (c.H + c.n_yseg - 1) / c.n_yseg;
+  c.ok = 1;
+  return true;
+}
+
+template <int CP>   // cout_pad: 16 or 32 (sizes the per-thread InstanceNorm partial sums)
+__global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const __grid_constant__ RowsArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const RowsCfg& c = p.c;
+  const ConvArgs& a = p.a;
+  uint8_t* w_s = smem;
+  uint8_t* ring = smem + c.w_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)c.stages * c.stage_bytes);   // [16]
+  uint64_t* empty_bar = full_bar + kRowsMaxStages;                                              // [16]
+  uint64_t* tfull_bar = empty_bar + kRowsMaxStages;                                             // [10]
+  uint64_t* tempty_bar = tfull_bar + kRowsMaxSlots;                                             // [10]
+  uint64_t* w_bar = tempty_bar + kRowsMaxSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* xs = reinterpret_cast<float*>(tmem_slot + 4);
+  float* xh = xs + a.cin;
+  float* xl = xh + a.cin;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&full_bar[s], kRowsGroupThreads);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < c.slots; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kRowsMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {   // resident weights: one bulk copy per CTA
+    mbar_expect_tx(w_bar, (uint32_t)c.w_bytes);
+    bulk_g2s(w_s, a.w_umma, (uint32_t)c.w_bytes, w_bar);
+  }
+
+  // unit u -> (sample b, plane z, y segment); rows [ya, yb)
+  auto decode = [&](int u, int& b, int& z, int& ya, int& yb) {
+    z = u % c.D;
+    u /= c.D;
+    const int seg = u % c.n_yseg;
+    b = u / c.n_yseg;
+    ya = seg * c.seg_rows;
+    yb = ya + c.seg_rows;
+    if (yb > c.H) yb = c.H;
+  };
+
+  if (warp < 8) {
+    // =========================== PRODUCERS ===========================
+    const int tid = threadIdx.x;
+    const int grp = tid / kRowsGroupThreads;          // stages are dealt round-robin to the 4 groups
+    const int gt = tid - grp * kRowsGroupThreads;
+    const int items_per_plane = c.Q * c.P_row;        // 16-byte items of one (kz) plane row, pads included
+    long long row_counter = 0;                        // global stage sequence number
+    int cur_b = -1;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int b, z, ya, yb;
+      decode(u, b, z, ya, yb);
+      if (b != cur_b) {
+        named_bar_sync(1, kRowsProducerThreads);
+        for (int ch = tid; ch < a.cin; ch += kRowsProducerThreads) {
+          float sc, sh;
+          const ChanMeta m = a.src_meta[ch];
+          xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + ch) * 2, m, a.src_inv_count, sc, sh);
+          xs[ch] = sc;
+          xh[ch] = sh;
+          xl[ch] = m.eps < 0.f ? 1.f : m.slope;
+        }
+        named_bar_sync(1, kRowsProducerThreads);
+        cur_b = b;
+      }
+      const int n_rows = (yb - ya) + 2;
+      for (int j = 0; j < n_rows; ++j, ++row_counter) {
+        if ((int)(row_counter % kRowsProducerGroups) != grp) continue;
+        const int stage = (int)(row_counter % c.stages);
+        const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = ring + (size_t)stage * c.stage_bytes;
+        const int y_in = ya - 1 + j;
+        const bool row_ok = y_in >= 0 && y_in < c.H;
+        for (int kz = 0; kz < c.nkz; ++kz) {
+          const int z_in = z + kz - c.pz;
+          if (z_in < 0 || z_in >= c.D) continue;      // the MMA warp skips this plane too
+          const __half* row = a.src + ((((size_t)b * c.D + z_in) * c.H + (row_ok ? y_in : 0)) * c.W) * a.src_cs;
+          uint8_t* dstp = st + (size_t)kz * c.Q * c.P_row * 16;
+          constexpr int U = 4;
+          for (int i0 = gt; i0 < items_per_plane; i0 += kRowsGroupThreads * U) {
+            uint4 raw[U];
+            int idx[U];
+            bool ok[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              const int i = i0 + k * kRowsGroupThreads;
+              // item i -> position xp = i / Q, 8-channel group q = i % Q (lanes sweep the channels of a voxel first,
+              // so a warp reads whole contiguous voxels)
+              const int xp = i / c.Q;
+              const int q = i - xp * c.Q;
+              const int x_in = xp - c.px;
+              idx[k] = (i < items_per_plane) ? (q * c.P_row + xp) : -1;
+              ok[k] = (i < items_per_plane) && row_ok && x_in >= 0 && x_in < c.W;
+              raw[k] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(row + (size_t)x_in * a.src_cs + q * 8));
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              if (idx[k] < 0) continue;
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);
+              if (ok[k]) {
+                const int i = i0 + k * kRowsGroupThreads;
+                const int ch0 = (i % c.Q) * 8;
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k]);
+                __half2 r2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(h2[e]);
+                  float v0 = fmaf(f.x, xs[ch0 + 2 * e], xh[ch0 + 2 * e]);
+                  float v1 = fmaf(f.y, xs[ch0 + 2 * e + 1], xh[ch0 + 2 * e + 1]);
+                  v0 = fmaxf(v0, v0 * xl[ch0 + 2 * e]);
+                  v1 = fmaxf(v1, v1 * xl[ch0 + 2 * e + 1]);
+                  r2[e] = __floats2half2_rn(v0, v1);
+                }
+                o = *reinterpret_cast<uint4*>(r2);
+              }
+              *reinterpret_cast<uint4*>(dstp + (size_t)idx[k] * 16) = o;
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[stage]);
+      }
+    }
+  } else if (warp == kRowsMmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    const bool leader = lane == 0;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(c.Nf >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_lbo = (uint32_t)c.P_row * 16, b_lbo = (uint32_t)c.Nf * 16;
+    const uint64_t a_desc0 = make_desc(0, a_lbo, 128);
+    const uint64_t b_desc0 = make_desc(smem_u32(w_s), b_lbo, 128);
+    const uint32_t ring_base = smem_u32(ring);
+    mbar_wait(w_bar, 0);
+    long long row_counter = 0;     // stage sequence
+    long long tile_counter = 0;    // TMEM slot sequence (one tile per input row)
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int b, z, ya, yb;
+      decode(u, b, z, ya, yb);
+      const int n_rows = (yb - ya) + 2;
+      for (int j = 0; j < n_rows; ++j, ++row_counter, ++tile_counter) {
+        const int stage = (int)(row_counter % c.stages);
+        const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
+        const int slot = (int)(tile_counter % c.slots);
+        const uint32_t sphase = (uint32_t)((tile_counter / c.slots) & 1);
+        mbar_wait(&tempty_bar[slot], sphase ^ 1);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(slot * c.Nf);
+        const uint32_t st_base = ring_base + (uint32_t)stage * (uint32_t)c.stage_bytes;
+        uint32_t accum = 0;
+        for (int kz = 0; kz < c.nkz; ++kz) {
+          const int z_in = z + kz - c.pz;
+          if (z_in < 0 || z_in >= c.D) continue;
+          for (int kx = 0; kx < c.nkx; ++kx) {
+            const uint64_t da0 = a_desc0 + (uint64_t)((st_base + (uint32_t)(kz * c.Q) * a_lbo + (uint32_t)kx * 16) >> 4);
+            const uint64_t db0 = b_desc0 + (uint64_t)(((uint32_t)((kz * c.nkx + kx) * c.chunks * 2) * b_lbo) >> 4);
+#pragma unroll 2
+            for (int kc = 0; kc < c.chunks; ++kc) {
+              const uint64_t da = da0 + (uint64_t)(((uint32_t)(kc * 2) * a_lbo) >> 4);
+              const uint64_t db = db0 + (uint64_t)(((uint32_t)(kc * 2) * b_lbo) >> 4);
+              if (leader) umma_f16(d, da, db, idesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        if (leader) {
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== EPILOGUE ===========================
+    const int wq = warp & 3;
+    const int x = wq * 32 + lane;                   // output column == TMEM lane
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
+    long long tile_counter = 0;
+    int cur_b = -1;
+    float s1[CP], s2[CP];
+#pragma unroll
+    for (int j = 0; j < CP; ++j) s1[j] = s2[j] = 0.f;
+    auto flush_stats = [&](int b) {
+      if (!a.dst_stats || b < 0) return;
+#pragma unroll
+      for (int j = 0; j < CP; ++j) {
+        float v1 = s1[j], v2 = s2[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+        }
+        if (lane == 0 && j < a.cout) {
+          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + j) * 2 + 0, (double)v1);
+          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + j) * 2 + 1, (double)v2);
+        }
+        s1[j] = s2[j] = 0.f;
+      }
+    };
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int b, z, ya, yb;
+      decode(u, b, z, ya, yb);
+      if (b != cur_b) {
+        flush_stats(cur_b);
+        cur_b = b;
+      }
+      const int n_out = yb - ya;
+      __half* out_plane = a.dst + (((size_t)b * c.D + z) * c.H) * c.W * a.dst_cs;
+      for (int yo = 0; yo < n_out; ++yo) {
+        // unit tiles yo, yo+1, yo+2 hold input rows y-1, y, y+1; MMAs complete in order: wait for the last
+        const long long t2 = tile_counter + yo + 2;
+        mbar_wait(&tfull_bar[(int)(t2 % c.slots)], (uint32_t)((t2 / c.slots) & 1));
+        tc_fence_after();
+        const int y = ya + yo;
+        const uint32_t t_a = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo) % c.slots) * c.Nf);
+        const uint32_t t_b = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 1) % c.slots) * c.Nf);
+        const uint32_t t_c = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 2) % c.slots) * c.Nf);
+#pragma unroll
+        for (int g0 = 0; g0 < CP; g0 += 16) {
+          // out(y) = D'[y-1][ky = 0] + D'[y][ky = 1] + D'[y+1][ky = 2]   (input row r feeds output row r - ky + 1)
+          uint32_t r0[16], r1[16];
+          tmem_ld16(t_a + (uint32_t)(0 * CP + g0), r0);
+          tmem_ld16(t_b + (uint32_t)(1 * CP + g0), r1);
+          float acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          tmem_ld16(t_c + (uint32_t)(2 * CP + g0), r0);
+          if (x < c.W) {
+            __half hv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float bj = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
+              hv[j] = __float2half_rn(acc[j] + __uint_as_float(r0[j]) + bj);
+              const float f = __half2float(hv[j]);
+              s1[g0 + j] += f;
+              s2[g0 + j] = fmaf(f, f, s2[g0 + j]);
+            }
+            __half* q = out_plane + ((size_t)y * c.W + x) * a.dst_cs + g0;
+            if (vec_store && g0 + 16 <= a.cout) {
+              reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
+              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (g0 + j < a.cout) q[j] = hv[j];
+            }
+          }
+        }
+        // unit tile yo is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[(int)((tile_counter + yo) % c.slots)]);
+      }
+      // the last two tiles of the unit have no later consumer
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
+      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
+      tile_counter += n_out + 2;
+    }
+    flush_stats(cur_b);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kRowsMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// weights [cout][cin][kz][ky][kx] fp32 -> fp16 [kz][kx][chunk][half][n = ky * cout_pad + co][8]
+__global__ void pack_weights_rows_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout,
+                                         int cout_pad, RowsCfg c) {
+  const size_t total = (size_t)c.nkz * c.nkx * c.chunks * 2 * c.Nf * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int e = (int)(r % 8); r /= 8;
+    const int n = (int)(r % c.Nf); r /= c.Nf;
+    const int h = (int)(r % 2); r /= 2;
+    const int kc = (int)(r % c.chunks); r /= c.chunks;
+    const int kx = (int)(r % c.nkx); r /= c.nkx;
+    const int kz = (int)r;
+    const int ky = n / cout_pad, co = n - ky * cout_pad;
+    const int ci = kc * 16 + h * 8 + e;
+    float v = 0.f;
+    if (co < cout) v = w[((((size_t)co * cin + ci) * c.nkz + kz) * 3 + ky) * c.nkx + kx];
+    out[i] = __float2half_rn(v);
+  }
+}
+
+bool rows_supported(const ConvArgs& a) {
+  RowsCfg c;
+  return plan_rows(a, c);
+}
+
+int launch_pack_weights_rows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s) {
+  RowsCfg c;
+  if (!plan_rows(a, c)) return FNNU_E_UNSUPPORTED;
+  const size_t total = (size_t)c.w_bytes / 2;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_rows_kernel<<<blocks, 256, 0, s>>>(w_dev, (__half*)out, a.cin, a.cout, a.cout_pad, c);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
+  RowsArgs p;
+  p.a = a;
+  if (!plan_rows(a, p.c)) {
+    set_error("conv_umma_rows: unsupported shape");
+    return FNNU_E_UNSUPPORTED;
+  }
+  p.n_units = a.batch * p.c.D * p.c.n_yseg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmemLimit));
+    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmemLimit));
+    attr_set = true;
+  }
+  int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  if (a.cout_pad == 16)
+    conv_umma_rows_kernel<16><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);
+  else
+    conv_umma_rows_kernel<32><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);
+  FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+}  // namespace fnnu

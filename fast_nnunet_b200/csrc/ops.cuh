@@ -16,7 +16,8 @@ struct ConvArgs {
   double* dst_stats;        // or nullptr (no InstanceNorm after this op)
   int dst_stat_stride;
   const float* w;           // direct kernel: [tap][cin][cout_pad] fp32
-  const void* w_umma;       // tcgen05 kernel: packed fp16 blob (see conv_umma.cu) or nullptr
+  const void* w_umma;       // tcgen05 kernels: packed fp16 blob (conv_umma.cu / conv_umma_rows.cu) or nullptr
+  int use_rows;             // w_umma is packed for the row-streaming kernel
   const float* bias;        // [cout] or nullptr
   int cin, cout, cout_pad;
   int in_d[3], out_d[3];
@@ -64,5 +65,10 @@ bool umma_supported(const ConvArgs& a);
 size_t umma_packed_weight_bytes(int cin, int cout, int ntaps, int transposed);
 int launch_pack_weights_umma(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_umma(const ConvArgs& a, cudaStream_t s);
+
+// row-streaming, ky-folded tcgen05 kernel for thin full-resolution layers (conv_umma_rows.cu)
+bool rows_supported(const ConvArgs& a);
+int launch_pack_weights_rows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
+int launch_conv_rows(const ConvArgs& a, cudaStream_t s);
 
 }  // namespace fnnu

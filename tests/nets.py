@@ -14,6 +14,13 @@ ANISO_PLAIN = dict(cls=M.PLAIN, in_ch=2, heads=5, patch=(20, 24, 32),
                                           [[1, 1, 1], [1, 2, 2], [2, 2, 2], [2, 1, 1]], [2, 1, 2, 2], [1, 2, 1]))
 SMALL_RESENC = dict(cls=M.RESENC, in_ch=4, heads=4, patch=(32, 32, 32),
                     kw=M.resenc_arch_kwargs([16, 32, 32], [[3, 3, 3]] * 3, [[1, 1, 1], [2, 2, 2], [2, 2, 2]], [1, 2, 2]))
+# shapes that exercise the row-streaming (ky-folded) tcgen05 kernel: W in [64, 128], Cout 16 / 32
+ROWS_W128 = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(8, 16, 128),
+                 kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
+ROWS_W96 = dict(cls=M.PLAIN, in_ch=2, heads=2, patch=(12, 20, 96),
+                kw=M.plain_arch_kwargs([16, 32], [[1, 3, 3], [3, 3, 3]], [[1, 1, 1], [1, 2, 2]]))
+ROWS_W64_C32 = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(8, 24, 64),
+                    kw=M.plain_arch_kwargs([32, 64], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
 STUDENT = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
                kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
 
