@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {   // resident weights: one bulk copy per CTA
-    mbar_expect_tx(w_bar, (uint32_t)c.w_bytes);
+    mbar_arrive_expect_tx(w_bar, (uint32_t)c.w_bytes);     // the barrier's single arrival + the byte count
     bulk_g2s(w_s, a.w_umma, (uint32_t)c.w_bytes, w_bar);
   }
 
