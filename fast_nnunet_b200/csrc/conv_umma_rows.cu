@@ -56,7 +56,7 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   if (a.transposed) return false;
   if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
   if (a.k[1] != 3) return false;                         // the folded axis
-  if (a.cin % 16 != 0 || a.cin < 16 || a.cin > 64) return false;
+  if (a.cin != 16 && a.cin != 32 && a.cin != 64) return false;   // Cin / 8 must be a power of two (producer mapping)
   if (a.cout_pad != 16 && a.cout_pad != 32) return false;   // per-thread InstanceNorm partials live in registers
   if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
   c.D = a.in_d[0]; c.H = a.in_d[1]; c.W = a.in_d[2];
@@ -150,28 +150,33 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     const int tid = threadIdx.x;
     const int grp = tid / kRowsGroupThreads;          // stages are dealt round-robin to the 4 groups
     const int gt = tid - grp * kRowsGroupThreads;
-    const int items_per_plane = c.Q * c.P_row;        // 16-byte items of one (kz) plane row, pads included
+    // Q is 2, 4 or 8: a thread owns ONE 8-channel group q (so its scale/shift/slope live in registers) and
+    // every (64 / Q)-th position; consecutive lanes read the consecutive 16-byte pieces of whole voxels.
+    const int qshift = c.Q == 2 ? 1 : (c.Q == 4 ? 2 : 3);
+    const int q = gt & (c.Q - 1);
+    const int xp0 = gt >> qshift;
+    const int xp_step = kRowsGroupThreads >> qshift;
+    constexpr int kMaxIt = 9;                          // ceil(P_row / xp_step) <= ceil(140 / 16)
+    const int n_it = (c.P_row + xp_step - 1) / xp_step;
     long long row_counter = 0;                        // global stage sequence number
     int cur_b = -1;
+    float sc[8], sh[8], sl[8];
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z, ya, yb;
       decode(u, b, z, ya, yb);
       if (b != cur_b) {
-        named_bar_sync(1, kRowsProducerThreads);
-        for (int ch = tid; ch < a.cin; ch += kRowsProducerThreads) {
-          float sc, sh;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = q * 8 + e;
           const ChanMeta m = a.src_meta[ch];
-          xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + ch) * 2, m, a.src_inv_count, sc, sh);
-          xs[ch] = sc;
-          xh[ch] = sh;
-          xl[ch] = m.eps < 0.f ? 1.f : m.slope;
+          xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + ch) * 2, m, a.src_inv_count, sc[e], sh[e]);
+          sl[e] = m.eps < 0.f ? 1.f : m.slope;
         }
-        named_bar_sync(1, kRowsProducerThreads);
         cur_b = b;
       }
       const int n_rows = (yb - ya) + 2;
       for (int j = 0; j < n_rows; ++j, ++row_counter) {
-        if ((int)(row_counter % kRowsProducerGroups) != grp) continue;
+        if ((int)(row_counter & (kRowsProducerGroups - 1)) != grp) continue;
         const int stage = (int)(row_counter % c.stages);
         const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -181,48 +186,38 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
         for (int kz = 0; kz < c.nkz; ++kz) {
           const int z_in = z + kz - c.pz;
           if (z_in < 0 || z_in >= c.D) continue;      // the MMA warp skips this plane too
-          const __half* row = a.src + ((((size_t)b * c.D + z_in) * c.H + (row_ok ? y_in : 0)) * c.W) * a.src_cs;
-          uint8_t* dstp = st + (size_t)kz * c.Q * c.P_row * 16;
-          constexpr int U = 4;
-          for (int i0 = gt; i0 < items_per_plane; i0 += kRowsGroupThreads * U) {
-            uint4 raw[U];
-            int idx[U];
-            bool ok[U];
+          const __half* row = a.src + ((((size_t)b * c.D + z_in) * c.H + (row_ok ? y_in : 0)) * c.W) * a.src_cs + q * 8;
+          uint8_t* dstp = st + ((size_t)(kz * c.Q + q) * c.P_row) * 16;
+          uint4 raw[kMaxIt];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              const int i = i0 + k * kRowsGroupThreads;
-              // item i -> position xp = i / Q, 8-channel group q = i % Q (lanes sweep the channels of a voxel first,
-              // so a warp reads whole contiguous voxels)
-              const int xp = i / c.Q;
-              const int q = i - xp * c.Q;
-              const int x_in = xp - c.px;
-              idx[k] = (i < items_per_plane) ? (q * c.P_row + xp) : -1;
-              ok[k] = (i < items_per_plane) && row_ok && x_in >= 0 && x_in < c.W;
-              raw[k] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(row + (size_t)x_in * a.src_cs + q * 8));
-            }
+          for (int it = 0; it < kMaxIt; ++it) {
+            const int xp = xp0 + it * xp_step;
+            const int x_in = xp - c.px;
+            raw[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (it < n_it && row_ok && x_in >= 0 && x_in < c.W)
+              raw[it] = __ldg(reinterpret_cast<const uint4*>(row + (size_t)x_in * a.src_cs));
+          }
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              if (idx[k] < 0) continue;
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[k]) {
-                const int i = i0 + k * kRowsGroupThreads;
-                const int ch0 = (i % c.Q) * 8;
-                const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k]);
-                __half2 r2[4];
+          for (int it = 0; it < kMaxIt; ++it) {
+            const int xp = xp0 + it * xp_step;
+            if (it >= n_it || xp >= c.P_row) continue;
+            const int x_in = xp - c.px;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok && x_in >= 0 && x_in < c.W) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[it]);
+              __half2 r2[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __half22float2(h2[e]);
-                  float v0 = fmaf(f.x, xs[ch0 + 2 * e], xh[ch0 + 2 * e]);
-                  float v1 = fmaf(f.y, xs[ch0 + 2 * e + 1], xh[ch0 + 2 * e + 1]);
-                  v0 = fmaxf(v0, v0 * xl[ch0 + 2 * e]);
-                  v1 = fmaxf(v1, v1 * xl[ch0 + 2 * e + 1]);
-                  r2[e] = __floats2half2_rn(v0, v1);
-                }
-                o = *reinterpret_cast<uint4*>(r2);
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                float v0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                float v1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                v0 = fmaxf(v0, v0 * sl[2 * e]);
+                v1 = fmaxf(v1, v1 * sl[2 * e + 1]);
+                r2[e] = __floats2half2_rn(v0, v1);
               }
-              *reinterpret_cast<uint4*>(dstp + (size_t)idx[k] * 16) = o;
+              o = *reinterpret_cast<uint4*>(r2);
             }
+            *reinterpret_cast<uint4*>(dstp + (size_t)xp * 16) = o;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -326,19 +321,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
 #pragma unroll
         for (int g0 = 0; g0 < CP; g0 += 16) {
           // out(y) = D'[y-1][ky = 0] + D'[y][ky = 1] + D'[y+1][ky = 2]   (input row r feeds output row r - ky + 1)
-          uint32_t r0[16], r1[16];
-          tmem_ld16(t_a + (uint32_t)(0 * CP + g0), r0);
-          tmem_ld16(t_b + (uint32_t)(1 * CP + g0), r1);
-          float acc[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-          tmem_ld16(t_c + (uint32_t)(2 * CP + g0), r0);
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16_nowait(t_a + (uint32_t)(0 * CP + g0), r0);
+          tmem_ld16_nowait(t_b + (uint32_t)(1 * CP + g0), r1);
+          tmem_ld16_nowait(t_c + (uint32_t)(2 * CP + g0), r2);
+          tmem_wait_ld();
           if (x < c.W) {
             __half hv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float bj = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
-              hv[j] = __float2half_rn(acc[j] + __uint_as_float(r0[j]) + bj);
+              hv[j] = __float2half_rn((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]) + bj);
               const float f = __half2float(hv[j]);
               s1[g0 + j] += f;
               s2[g0 + j] = fmaf(f, f, s2[g0 + j]);
