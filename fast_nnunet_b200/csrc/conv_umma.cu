@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
             bulk_g2s(b_s, wsrc, (uint32_t)c.b_stage_bytes, &full_bar[stage]);
           }
           const int ch0 = g * c.KC * 16 + q * 8;
-          float sc[8], sh[8], sl[8];
+          __half2 s2[4], t2[4], l2[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            sc[e] = xs[ch0 + e];
-            sh[e] = xh[ch0 + e];
-            sl[e] = xl[ch0 + e];
+          for (int e = 0; e < 4; ++e) {
+            s2[e] = __floats2half2_rn(xs[ch0 + 2 * e], xs[ch0 + 2 * e + 1]);
+            t2[e] = __floats2half2_rn(xh[ch0 + 2 * e], xh[ch0 + 2 * e + 1]);
+            l2[e] = __floats2half2_rn(xl[ch0 + 2 * e], xl[ch0 + 2 * e + 1]);
           }
           for (int phy = 0; phy < c.nph_y; ++phy) {
             for (int phx = 0; phx < c.nph_x; ++phx) {
@@ -325,18 +325,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
                   if (pos[k] < 0) continue;
                   uint4 o = make_uint4(0u, 0u, 0u, 0u);
                   if (ok[k]) {
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k]);
-                    __half2 r2[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      float2 f = __half22float2(h2[e]);
-                      float v0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                      float v1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                      v0 = fmaxf(v0, v0 * sl[2 * e]);
-                      v1 = fmaxf(v1, v1 * sl[2 * e + 1]);
-                      r2[e] = __floats2half2_rn(v0, v1);
-                    }
-                    o = *reinterpret_cast<uint4*>(r2);
+                    o = xform8_h2(raw[k], s2, t2, l2);
                   }
                   *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
                 }
@@ -382,6 +371,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + (size_t)stage * stage_bytes);
           const uint32_t b_base = a_base + (uint32_t)c.a_stage_bytes;
+          if (leader) {
           for (int kc = 0; kc < c.KC; ++kc) {
             for (int t = 0; t < c.ntyx; ++t) {
               const uint64_t db = b_desc0 + (uint64_t)((b_base + (uint32_t)((kc * c.ntyx + t) * 2) * b_lbo) >> 4);
@@ -395,7 +385,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
                 uint64_t da = da_row;
 #pragma unroll 4
                 for (int j = 0; j < n_inner; ++j) {
-                  if (leader) umma_f16(d, da, db, idesc, accum);
+                  umma_f16(d, da, db, idesc, accum);
                   d += (uint32_t)c.Nc;
                   da += inner_step;
                 }
@@ -403,7 +393,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
               }
             }
           }
-          if (leader) umma_commit(&empty_bar[stage]);
+          umma_commit(&empty_bar[stage]);
+          }
           __syncwarp();
           first = false;
           if (++stage == c.stages) { stage = 0; phase ^= 1; }

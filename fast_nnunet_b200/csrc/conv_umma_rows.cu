@@ -55,7 +55,7 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   memset(&c, 0, sizeof(c));
   if (a.transposed) return false;
   if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
-  if (a.k[1] != 3) return false;                         // the folded axis
+  if (a.k[1] != 3 || a.k[2] != 3) return false;          // ky is the folded axis; kx == 3 fixes the row pitch (140)
   if (a.cin != 16 && a.cin != 32 && a.cin != 64) return false;   // Cin / 8 must be a power of two (producer mapping)
   if (a.cout_pad != 16 && a.cout_pad != 32) return false;   // per-thread InstanceNorm partials live in registers
   if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
@@ -88,7 +88,7 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   return true;
 }
 
-template <int CP>   // cout_pad: 16 or 32 (sizes the per-thread InstanceNorm partial sums)
+template <int CP, int CHUNKS>   // cout_pad (16 | 32) sizes the per-thread InstanceNorm partials; CHUNKS = Cin / 16
 __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const __grid_constant__ RowsArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const RowsCfg& c = p.c;
@@ -160,17 +160,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     const int n_it = (c.P_row + xp_step - 1) / xp_step;
     long long row_counter = 0;                        // global stage sequence number
     int cur_b = -1;
-    float sc[8], sh[8], sl[8];
+    __half2 s2[4], t2[4], l2[4];
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z, ya, yb;
       decode(u, b, z, ya, yb);
       if (b != cur_b) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ch = q * 8 + e;
-          const ChanMeta m = a.src_meta[ch];
-          xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + ch) * 2, m, a.src_inv_count, sc[e], sh[e]);
-          sl[e] = m.eps < 0.f ? 1.f : m.slope;
+        for (int e = 0; e < 4; ++e) {
+          float sc[2], sh[2], sl[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int ch = q * 8 + 2 * e + k;
+            const ChanMeta m = a.src_meta[ch];
+            xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + ch) * 2, m, a.src_inv_count, sc[k], sh[k]);
+            sl[k] = m.eps < 0.f ? 1.f : m.slope;
+          }
+          s2[e] = __floats2half2_rn(sc[0], sc[1]);
+          t2[e] = __floats2half2_rn(sh[0], sh[1]);
+          l2[e] = __floats2half2_rn(sl[0], sl[1]);
         }
         cur_b = b;
       }
@@ -204,18 +211,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
             const int x_in = xp - c.px;
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (row_ok && x_in >= 0 && x_in < c.W) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[it]);
-              __half2 r2[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(h2[e]);
-                float v0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                float v1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                v0 = fmaxf(v0, v0 * sl[2 * e]);
-                v1 = fmaxf(v1, v1 * sl[2 * e + 1]);
-                r2[e] = __floats2half2_rn(v0, v1);
-              }
-              o = *reinterpret_cast<uint4*>(r2);
+              o = xform8_h2(raw[it], s2, t2, l2);
             }
             *reinterpret_cast<uint4*>(dstp + (size_t)xp * 16) = o;
           }
@@ -226,50 +222,56 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     }
   } else if (warp == kRowsMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    const bool leader = lane == 0;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(c.Nf >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a_lbo = (uint32_t)c.P_row * 16, b_lbo = (uint32_t)c.Nf * 16;
-    const uint64_t a_desc0 = make_desc(0, a_lbo, 128);
-    const uint64_t b_desc0 = make_desc(smem_u32(w_s), b_lbo, 128);
-    const uint32_t ring_base = smem_u32(ring);
+    // One elected lane issues; every descriptor offset of a row's 9 * CHUNKS MMAs is a compile-time constant
+    // added to the stage base, so the issue path is ~a dozen instructions per MMA (the MMA itself occupies the
+    // tensor pipe for ~64 cycles of operand fetch).
+    constexpr uint32_t kProw = 140;                      // plan_rows: nkx == 3 -> P_row == 140
+    constexpr uint32_t kNf = 3 * CP;
+    constexpr uint32_t kQ = 2 * CHUNKS;
+    const uint32_t idesc = (1u << 4) | ((kNf >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t a_desc0 = make_desc(smem_u32(ring), kProw * 16, 128);
+    const uint64_t b_desc0 = make_desc(smem_u32(w_s), kNf * 16, 128);
+    const uint32_t stage_u16 = (uint32_t)c.stage_bytes >> 4;
     mbar_wait(w_bar, 0);
-    long long row_counter = 0;     // stage sequence
-    long long tile_counter = 0;    // TMEM slot sequence (one tile per input row)
+    int stage = 0, slot = 0;
+    uint32_t phase = 0, sphase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z, ya, yb;
       decode(u, b, z, ya, yb);
       const int n_rows = (yb - ya) + 2;
-      for (int j = 0; j < n_rows; ++j, ++row_counter, ++tile_counter) {
-        const int stage = (int)(row_counter % c.stages);
-        const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
-        const int slot = (int)(tile_counter % c.slots);
-        const uint32_t sphase = (uint32_t)((tile_counter / c.slots) & 1);
+      bool kzv[3];
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) kzv[kz] = kz < c.nkz && (z + kz - c.pz) >= 0 && (z + kz - c.pz) < c.D;
+      for (int j = 0; j < n_rows; ++j) {
         mbar_wait(&tempty_bar[slot], sphase ^ 1);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(slot * c.Nf);
-        const uint32_t st_base = ring_base + (uint32_t)stage * (uint32_t)c.stage_bytes;
-        uint32_t accum = 0;
-        for (int kz = 0; kz < c.nkz; ++kz) {
-          const int z_in = z + kz - c.pz;
-          if (z_in < 0 || z_in >= c.D) continue;
-          for (int kx = 0; kx < c.nkx; ++kx) {
-            const uint64_t da0 = a_desc0 + (uint64_t)((st_base + (uint32_t)(kz * c.Q) * a_lbo + (uint32_t)kx * 16) >> 4);
-            const uint64_t db0 = b_desc0 + (uint64_t)(((uint32_t)((kz * c.nkx + kx) * c.chunks * 2) * b_lbo) >> 4);
-#pragma unroll 2
-            for (int kc = 0; kc < c.chunks; ++kc) {
-              const uint64_t da = da0 + (uint64_t)(((uint32_t)(kc * 2) * a_lbo) >> 4);
-              const uint64_t db = db0 + (uint64_t)(((uint32_t)(kc * 2) * b_lbo) >> 4);
-              if (leader) umma_f16(d, da, db, idesc, accum);
-              accum = 1;
+        if (lane == 0) {
+          const uint32_t d = tmem_base + (uint32_t)slot * kNf;
+          const uint64_t da_st = a_desc0 + (uint64_t)((uint32_t)stage * stage_u16);
+          uint32_t accum = 0;
+#pragma unroll
+          for (int kz = 0; kz < 3; ++kz) {
+            if (!kzv[kz]) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (int kc = 0; kc < CHUNKS; ++kc) {
+                constexpr uint32_t dummy = 0;
+                (void)dummy;
+                const uint32_t a_off = (uint32_t)((kz * (int)kQ + kc * 2) * (int)kProw + kx);
+                const uint32_t b_off = (uint32_t)((((kz * 3 + kx) * CHUNKS + kc) * 2) * (int)kNf);
+                umma_f16(d, da_st + a_off, b_desc0 + b_off, idesc, accum);
+                accum = 1;
+              }
             }
           }
-        }
-        if (leader) {
           umma_commit(&empty_bar[stage]);
           umma_commit(&tfull_bar[slot]);
         }
         __syncwarp();
+        if (++stage == c.stages) { stage = 0; phase ^= 1; }
+        if (++slot == c.slots) { slot = 0; sphase ^= 1; }
       }
     }
   } else {
@@ -411,17 +413,28 @@ int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
     return FNNU_E_UNSUPPORTED;
   }
   p.n_units = a.batch * p.c.D * p.c.n_yseg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmemLimit));
-    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmemLimit));
-    attr_set = true;
-  }
   int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-  if (a.cout_pad == 16)
-    conv_umma_rows_kernel<16><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);
-  else
-    conv_umma_rows_kernel<32><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);
+#define FNNU_ROWS_CASE(CPV, CHV)                                                                                    \
+  if (a.cout_pad == CPV && p.c.chunks == CHV) {                                                                      \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<CPV, CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     kRowsSmemLimit));                                                               \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    conv_umma_rows_kernel<CPV, CHV><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);                                   \
+  }
+  FNNU_ROWS_CASE(16, 1)
+  else FNNU_ROWS_CASE(16, 2)
+  else FNNU_ROWS_CASE(16, 4)
+  else FNNU_ROWS_CASE(32, 1)
+  else FNNU_ROWS_CASE(32, 2)
+  else FNNU_ROWS_CASE(32, 4)
+  else {
+    set_error("conv_umma_rows: no instantiation for cout_pad=%d chunks=%d", a.cout_pad, p.c.chunks);
+    return FNNU_E_UNSUPPORTED;
+  }
+#undef FNNU_ROWS_CASE
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }

@@ -1,6 +1,7 @@
 // Inline-PTX building blocks shared by the tcgen05 kernels (sm_100a): mbarrier, bulk async copy (TMA
 // engine), UMMA shared-memory descriptors, tcgen05.mma / commit / ld, fences, named barriers.
 #pragma once
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace fnnu {
@@ -74,5 +75,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// Normalise-on-load of 8 fp16 channels: y = lrelu(x * scale + shift) in packed half2 arithmetic
+// (one HFMA2 + HMUL2 + HMNMX2 per channel pair).  slope in (0, 1]: max(v, slope * v) is LeakyReLU, slope 1 = identity.
+__device__ __forceinline__ uint4 xform8_h2(const uint4 raw, const __half2* s2, const __half2* t2, const __half2* l2) {
+  const __half2* x = reinterpret_cast<const __half2*>(&raw);
+  uint4 o;
+  __half2* y = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 v = __hfma2(x[e], s2[e], t2[e]);
+    y[e] = __hmax2(v, __hmul2(v, l2[e]));
+  }
+  return o;
+}
 
 }  // namespace fnnu
