@@ -56,7 +56,7 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   if (a.transposed) return false;
   if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
   if (a.k[1] != 3 || a.k[2] != 3) return false;          // ky is the folded axis; kx == 3 fixes the row pitch (140)
-  if (a.cin != 16 && a.cin != 32 && a.cin != 64) return false;   // Cin / 8 must be a power of two (producer mapping)
+  if (a.cin != 16 && a.cin != 32) return false;          // producer mapping: 64 threads cover a row in <= 9 steps
   if (a.cout_pad != 16 && a.cout_pad != 32) return false;   // per-thread InstanceNorm partials live in registers
   if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
   c.D = a.in_d[0]; c.H = a.in_d[1]; c.W = a.in_d[2];
@@ -161,10 +161,38 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     long long row_counter = 0;                        // global stage sequence number
     int cur_b = -1;
     __half2 s2[4], t2[4], l2[4];
+    // Software pipeline, two stages deep per group: the raw row is fetched with cp.async (zero-filled outside the
+    // image, no registers held, latency overlapped with the previous stage's transform), then normalised in place.
+    int pend_stage = -1, pend_mask = 0;               // stage whose copies are in flight; bit kz = plane present,
+    bool pend_row_ok = false;                         // bit 3.. unused
+    auto finish_pending = [&](int keep_in_flight) {
+      if (pend_stage < 0) return;
+      if (keep_in_flight) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+      if (pend_row_ok) {
+        uint8_t* st = ring + (size_t)pend_stage * c.stage_bytes;
+        for (int kz = 0; kz < c.nkz; ++kz) {
+          if (!((pend_mask >> kz) & 1)) continue;
+          uint8_t* dstp = st + ((size_t)(kz * c.Q + q) * c.P_row) * 16;
+#pragma unroll
+          for (int it = 0; it < kMaxIt; ++it) {
+            const int xp = xp0 + it * xp_step;
+            const int x_in = xp - c.px;
+            if (it < n_it && x_in >= 0 && x_in < c.W) {
+              uint4* ptr = reinterpret_cast<uint4*>(dstp + (size_t)xp * 16);
+              *ptr = xform8_h2(*ptr, s2, t2, l2);
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&full_bar[pend_stage]);
+      pend_stage = -1;
+    };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z, ya, yb;
       decode(u, b, z, ya, yb);
       if (b != cur_b) {
+        finish_pending(0);                            // rows of the previous sample use the previous transform
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float sc[2], sh[2], sl[2];
@@ -181,6 +209,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
         }
         cur_b = b;
       }
+      int zmask = 0;
+      for (int kz = 0; kz < c.nkz; ++kz)
+        if (z + kz - c.pz >= 0 && z + kz - c.pz < c.D) zmask |= 1 << kz;
       const int n_rows = (yb - ya) + 2;
       for (int j = 0; j < n_rows; ++j, ++row_counter) {
         if ((int)(row_counter & (kRowsProducerGroups - 1)) != grp) continue;
@@ -191,35 +222,27 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
         const int y_in = ya - 1 + j;
         const bool row_ok = y_in >= 0 && y_in < c.H;
         for (int kz = 0; kz < c.nkz; ++kz) {
+          if (!((zmask >> kz) & 1)) continue;         // the MMA warp skips this plane too
           const int z_in = z + kz - c.pz;
-          if (z_in < 0 || z_in >= c.D) continue;      // the MMA warp skips this plane too
           const __half* row = a.src + ((((size_t)b * c.D + z_in) * c.H + (row_ok ? y_in : 0)) * c.W) * a.src_cs + q * 8;
-          uint8_t* dstp = st + ((size_t)(kz * c.Q + q) * c.P_row) * 16;
-          uint4 raw[kMaxIt];
-#pragma unroll
-          for (int it = 0; it < kMaxIt; ++it) {
-            const int xp = xp0 + it * xp_step;
-            const int x_in = xp - c.px;
-            raw[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (it < n_it && row_ok && x_in >= 0 && x_in < c.W)
-              raw[it] = __ldg(reinterpret_cast<const uint4*>(row + (size_t)x_in * a.src_cs));
-          }
+          const uint32_t dsts = smem_u32(st + ((size_t)(kz * c.Q + q) * c.P_row) * 16);
 #pragma unroll
           for (int it = 0; it < kMaxIt; ++it) {
             const int xp = xp0 + it * xp_step;
             if (it >= n_it || xp >= c.P_row) continue;
             const int x_in = xp - c.px;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok && x_in >= 0 && x_in < c.W) {
-              o = xform8_h2(raw[it], s2, t2, l2);
-            }
-            *reinterpret_cast<uint4*>(dstp + (size_t)xp * 16) = o;
+            const bool ok = row_ok && x_in >= 0 && x_in < c.W;
+            cp_async16_zfill(dsts + (uint32_t)xp * 16, row + (size_t)(ok ? x_in : 0) * a.src_cs, ok ? 16u : 0u);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&full_bar[stage]);
+        cp_async_commit_group();
+        finish_pending(1);
+        pend_stage = stage;
+        pend_mask = zmask;
+        pend_row_ok = row_ok;
       }
     }
+    finish_pending(0);
   } else if (warp == kRowsMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // One elected lane issues; every descriptor offset of a row's 9 * CHUNKS MMAs is a compile-time constant
@@ -426,10 +449,8 @@ int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
   }
   FNNU_ROWS_CASE(16, 1)
   else FNNU_ROWS_CASE(16, 2)
-  else FNNU_ROWS_CASE(16, 4)
   else FNNU_ROWS_CASE(32, 1)
   else FNNU_ROWS_CASE(32, 2)
-  else FNNU_ROWS_CASE(32, 4)
   else {
     set_error("conv_umma_rows: no instantiation for cout_pad=%d chunks=%d", a.cout_pad, p.c.chunks);
     return FNNU_E_UNSUPPORTED;

@@ -76,6 +76,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 
+// Ampere-style asynchronous 16-byte copy global -> shared; src_bytes < 16 zero-fills the remainder.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Normalise-on-load of 8 fp16 channels: y = lrelu(x * scale + shift) in packed half2 arithmetic
 // (one HFMA2 + HMUL2 + HMNMX2 per channel pair).  slope in (0, 1]: max(v, slope * v) is LeakyReLU, slope 1 = identity.
 __device__ __forceinline__ uint4 xform8_h2(const uint4 raw, const __half2* s2, const __half2* t2, const __half2* l2) {
