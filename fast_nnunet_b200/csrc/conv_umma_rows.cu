@@ -150,35 +150,48 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     const int tid = threadIdx.x;
     const int grp = tid / kRowsGroupThreads;          // stages are dealt round-robin to the 4 groups
     const int gt = tid - grp * kRowsGroupThreads;
-    // Q is 2, 4 or 8: a thread owns ONE 8-channel group q (so its scale/shift/slope live in registers) and
-    // every (64 / Q)-th position; consecutive lanes read the consecutive 16-byte pieces of whole voxels.
-    const int qshift = c.Q == 2 ? 1 : (c.Q == 4 ? 2 : 3);
-    const int q = gt & (c.Q - 1);
-    const int xp0 = gt >> qshift;
-    const int xp_step = kRowsGroupThreads >> qshift;
-    constexpr int kMaxIt = 9;                          // ceil(P_row / xp_step) <= ceil(140 / 16)
-    const int n_it = (c.P_row + xp_step - 1) / xp_step;
+    // A thread owns ONE 8-channel group q (its scale/shift/slope live in registers) and every XP_STEP-th
+    // position of a row; consecutive lanes fetch the consecutive 16-byte pieces of whole voxels.  Everything
+    // that does not depend on the row (offsets, in-image flags) is computed once, so the per-row loop is
+    // one cp.async per item and, one stage later, LDS.128 + 12 half2 ops + STS.128 per item.
+    constexpr int kQ_ = 2 * CHUNKS;
+    constexpr int XP_STEP = kRowsGroupThreads / kQ_;          // 32 (Cin 16) or 16 (Cin 32)
+    constexpr int N_IT = (140 + XP_STEP - 1) / XP_STEP;       // 5 or 9
+    const int q = gt & (kQ_ - 1);
+    const int xp0 = gt / kQ_;
+    uint32_t goff[N_IT];                                      // byte offset of the voxel within its row
+    uint32_t live = 0, inimg = 0;                             // bit it: position exists / lies inside the image
+#pragma unroll
+    for (int it = 0; it < N_IT; ++it) {
+      const int xp = xp0 + it * XP_STEP;
+      const int x_in = xp - c.px;
+      const bool in = x_in >= 0 && x_in < c.W;
+      if (xp < c.P_row) live |= 1u << it;
+      if (in) inimg |= 1u << it;
+      goff[it] = (uint32_t)((in ? x_in : 0) * a.src_cs + q * 8) * 2u;
+    }
+    const uint32_t plane_bytes = (uint32_t)(c.Q * c.P_row) * 16u;
+    const uint32_t my_off = (uint32_t)(q * c.P_row + xp0) * 16u;   // this thread's first item inside a plane
+    const size_t row_bytes = (size_t)c.W * a.src_cs * 2;
     long long row_counter = 0;                        // global stage sequence number
     int cur_b = -1;
     __half2 s2[4], t2[4], l2[4];
     // Software pipeline, two stages deep per group: the raw row is fetched with cp.async (zero-filled outside the
     // image, no registers held, latency overlapped with the previous stage's transform), then normalised in place.
-    int pend_stage = -1, pend_mask = 0;               // stage whose copies are in flight; bit kz = plane present,
-    bool pend_row_ok = false;                         // bit 3.. unused
+    int pend_stage = -1, pend_mask = 0;               // stage whose copies are in flight; bit kz = plane present
+    bool pend_row_ok = false;
     auto finish_pending = [&](int keep_in_flight) {
       if (pend_stage < 0) return;
       if (keep_in_flight) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
       if (pend_row_ok) {
-        uint8_t* st = ring + (size_t)pend_stage * c.stage_bytes;
-        for (int kz = 0; kz < c.nkz; ++kz) {
-          if (!((pend_mask >> kz) & 1)) continue;
-          uint8_t* dstp = st + ((size_t)(kz * c.Q + q) * c.P_row) * 16;
+        uint8_t* st = ring + (size_t)pend_stage * c.stage_bytes + my_off;
 #pragma unroll
-          for (int it = 0; it < kMaxIt; ++it) {
-            const int xp = xp0 + it * xp_step;
-            const int x_in = xp - c.px;
-            if (it < n_it && x_in >= 0 && x_in < c.W) {
-              uint4* ptr = reinterpret_cast<uint4*>(dstp + (size_t)xp * 16);
+        for (int kz = 0; kz < 3; ++kz) {
+          if (!((pend_mask >> kz) & 1)) continue;
+#pragma unroll
+          for (int it = 0; it < N_IT; ++it) {
+            if ((inimg >> it) & 1) {
+              uint4* ptr = reinterpret_cast<uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16));
               *ptr = xform8_h2(*ptr, s2, t2, l2);
             }
           }
@@ -213,26 +226,25 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
       for (int kz = 0; kz < c.nkz; ++kz)
         if (z + kz - c.pz >= 0 && z + kz - c.pz < c.D) zmask |= 1 << kz;
       const int n_rows = (yb - ya) + 2;
+      const char* plane0 = reinterpret_cast<const char*>(a.src) + (((size_t)b * c.D + (z - c.pz)) * c.H) * row_bytes;
       for (int j = 0; j < n_rows; ++j, ++row_counter) {
         if ((int)(row_counter & (kRowsProducerGroups - 1)) != grp) continue;
         const int stage = (int)(row_counter % c.stages);
         const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = ring + (size_t)stage * c.stage_bytes;
         const int y_in = ya - 1 + j;
         const bool row_ok = y_in >= 0 && y_in < c.H;
-        for (int kz = 0; kz < c.nkz; ++kz) {
-          if (!((zmask >> kz) & 1)) continue;         // the MMA warp skips this plane too
-          const int z_in = z + kz - c.pz;
-          const __half* row = a.src + ((((size_t)b * c.D + z_in) * c.H + (row_ok ? y_in : 0)) * c.W) * a.src_cs + q * 8;
-          const uint32_t dsts = smem_u32(st + ((size_t)(kz * c.Q + q) * c.P_row) * 16);
+        const uint32_t fill = row_ok ? inimg : 0u;    // items that carry data; the rest are zero-filled
+        const uint32_t dst0 = smem_u32(ring + (size_t)stage * c.stage_bytes) + my_off;
+        const char* row0 = plane0 + (size_t)(row_ok ? y_in : 0) * row_bytes;
 #pragma unroll
-          for (int it = 0; it < kMaxIt; ++it) {
-            const int xp = xp0 + it * xp_step;
-            if (it >= n_it || xp >= c.P_row) continue;
-            const int x_in = xp - c.px;
-            const bool ok = row_ok && x_in >= 0 && x_in < c.W;
-            cp_async16_zfill(dsts + (uint32_t)xp * 16, row + (size_t)(ok ? x_in : 0) * a.src_cs, ok ? 16u : 0u);
+        for (int kz = 0; kz < 3; ++kz) {
+          if (!((zmask >> kz) & 1)) continue;         // the MMA warp skips this plane too
+          const char* row = row0 + (size_t)kz * c.H * row_bytes;
+#pragma unroll
+          for (int it = 0; it < N_IT; ++it) {
+            if ((live >> it) & 1)
+              cp_async16_zfill(dst0 + kz * plane_bytes + it * (XP_STEP * 16), row + goff[it], ((fill >> it) & 1) ? 16u : 0u);
           }
         }
         cp_async_commit_group();
@@ -305,9 +317,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
     long long tile_counter = 0;
     int cur_b = -1;
-    float s1[CP], s2[CP];
+    constexpr int kBiasRegs = CP == 16 ? 16 : 1;      // CP == 32: registers are needed for the partial sums
+    float s1[CP], s2[CP], bias[kBiasRegs];
 #pragma unroll
     for (int j = 0; j < CP; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBiasRegs; ++j) bias[j] = (a.bias && j < a.cout) ? __ldg(a.bias + j) : 0.f;
+    const bool col_ok = x < c.W;
+    const size_t out_row_stride = (size_t)c.W * a.dst_cs;
     auto flush_stats = [&](int b) {
       if (!a.dst_stats || b < 0) return;
 #pragma unroll
@@ -333,13 +350,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
         cur_b = b;
       }
       const int n_out = yb - ya;
-      __half* out_plane = a.dst + (((size_t)b * c.D + z) * c.H) * c.W * a.dst_cs;
-      for (int yo = 0; yo < n_out; ++yo) {
+      __half* out_px = a.dst + (((size_t)b * c.D + z) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs;
+      for (int yo = 0; yo < n_out; ++yo, out_px += out_row_stride) {
         // unit tiles yo, yo+1, yo+2 hold input rows y-1, y, y+1; MMAs complete in order: wait for the last
         const long long t2 = tile_counter + yo + 2;
         mbar_wait(&tfull_bar[(int)(t2 % c.slots)], (uint32_t)((t2 / c.slots) & 1));
         tc_fence_after();
-        const int y = ya + yo;
         const uint32_t t_a = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo) % c.slots) * c.Nf);
         const uint32_t t_b = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 1) % c.slots) * c.Nf);
         const uint32_t t_c = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 2) % c.slots) * c.Nf);
@@ -351,17 +367,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
           tmem_ld16_nowait(t_b + (uint32_t)(1 * CP + g0), r1);
           tmem_ld16_nowait(t_c + (uint32_t)(2 * CP + g0), r2);
           tmem_wait_ld();
-          if (x < c.W) {
+          if (col_ok) {
             __half hv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float bj = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
+              float bj;
+              if constexpr (CP == 16) bj = bias[j];
+              else bj = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
               hv[j] = __float2half_rn((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]) + bj);
               const float f = __half2float(hv[j]);
               s1[g0 + j] += f;
               s2[g0 + j] = fmaf(f, f, s2[g0 + j]);
             }
-            __half* q = out_plane + ((size_t)y * c.W + x) * a.dst_cs + g0;
+            __half* q = out_px + g0;
             if (vec_store && g0 + 16 <= a.cout) {
               reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
               reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
