@@ -253,54 +253,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 
   if (warp < kProducerWarps) {
     // =========================== PRODUCERS ===========================
-    // Thread -> one 8-channel group q and every LP-th position of a block row.  Raw fp16 arrives by cp.async
-    // (zero-filled outside the image / in the padding) one stage ahead; the previous stage is then normalised in
-    // place (LDS.128 + half2 math + STS.128) and published.  Per-item work is one address add and one cp.async.
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
     const int qshift = (Q == 2) ? 1 : (Q == 4 ? 2 : 3);
     const int q = tid & (Q - 1);
-    const int lpos = tid >> qshift;
-    const int LP = kProducerThreads >> qshift;            // positions covered per pass
-    const int n_pass = (c.pitch + LP - 1) / LP;
-    const size_t in_row_bytes = (size_t)Win * a.src_cs * 2;
-    const uint32_t q_off = (uint32_t)q * (uint32_t)c.P_alloc * 16u;
+    const int items = c.P_fill << qshift;
     int stage = 0;
     uint32_t phase = 0;
     int cur_b = -1;
-    // pending stage (copies in flight)
-    int pend_stage = -1, pend_y0 = 0;
-    __half2 ps2[4], pt2[4], pl2[4];
-    auto finish_pending = [&](int keep_in_flight) {
-      if (pend_stage < 0) return;
-      if (keep_in_flight) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-      uint8_t* a_q = ring + (size_t)pend_stage * stage_bytes + q_off;
-      for (int phy = 0; phy < c.nph_y; ++phy) {
-        for (int phx = 0; phx < c.nph_x; ++phx) {
-          uint8_t* pl = a_q + (size_t)(phy * c.nph_x + phx) * c.P_plane * 16;
-          for (int r = 0; r < c.R; ++r) {
-            const int y_in = c.sy * (pend_y0 + r - c.lead_y) + phy;
-            if (y_in < 0 || y_in >= Hin) continue;
-            uint8_t* row_s = pl + (size_t)r * c.pitch * 16;
-            for (int ps = 0; ps < n_pass; ++ps) {
-              const int xp = lpos + ps * LP;
-              const int x_in = c.sx * (xp - c.lead_x) + phx;
-              if (xp < c.pitch && x_in >= 0 && x_in < Win) {
-                uint4* ptr = reinterpret_cast<uint4*>(row_s + (size_t)xp * 16);
-                *ptr = xform8_h2(*ptr, ps2, pt2, pl2);
-              }
-            }
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&full_bar[pend_stage]);
-      pend_stage = -1;
-    };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const UnitIdx ui = decode_unit(p, u);
       if (ui.b != cur_b) {
-        finish_pending(0);
         named_bar_sync(1, kProducerThreads);
         for (int ch = tid; ch < a.cin; ch += kProducerThreads) {
           float sc, sh;
@@ -317,7 +280,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
       for (int kz = 0; kz < c.nkz; ++kz) {
         const int z_in = ui.z * c.sz + kz - c.pz;
         if (z_in < 0 || z_in >= Din) continue;
-        const char* plane = reinterpret_cast<const char*>(a.src) + ((size_t)ui.b * Din + z_in) * Hin * in_row_bytes;
+        const __half* plane = a.src + ((size_t)ui.b * Din + z_in) * Hin * Win * a.src_cs;
         for (int g = 0; g < c.G; ++g) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_s = ring + (size_t)stage * stage_bytes;
@@ -329,40 +292,52 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
             bulk_g2s(b_s, wsrc, (uint32_t)c.b_stage_bytes, &full_bar[stage]);
           }
           const int ch0 = g * c.KC * 16 + q * 8;
-          const uint32_t a_q = smem_u32(a_s) + q_off;
+          __half2 s2[4], t2[4], l2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            s2[e] = __floats2half2_rn(xs[ch0 + 2 * e], xs[ch0 + 2 * e + 1]);
+            t2[e] = __floats2half2_rn(xh[ch0 + 2 * e], xh[ch0 + 2 * e + 1]);
+            l2[e] = __floats2half2_rn(xl[ch0 + 2 * e], xl[ch0 + 2 * e + 1]);
+          }
           for (int phy = 0; phy < c.nph_y; ++phy) {
             for (int phx = 0; phx < c.nph_x; ++phx) {
-              const uint32_t pl = a_q + (uint32_t)((phy * c.nph_x + phx) * c.P_plane) * 16u;
-              for (int r = 0; r < c.R; ++r) {
-                const int y_in = c.sy * (y0 + r - c.lead_y) + phy;
-                const bool row_ok = y_in >= 0 && y_in < Hin;
-                const char* row_g = plane + (size_t)(row_ok ? y_in : 0) * in_row_bytes + (size_t)ch0 * 2;
-                const uint32_t row_s = pl + (uint32_t)(r * c.pitch) * 16u;
-                for (int ps = 0; ps < n_pass; ++ps) {
-                  const int xp = lpos + ps * LP;
-                  if (xp >= c.pitch) break;
+              uint8_t* a_q = a_s + ((size_t)q * c.P_alloc + (size_t)(phy * c.nph_x + phx) * c.P_plane) * 16;
+              constexpr int U = 8;
+              for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
+                uint4 raw[U];
+                int pos[U];
+                bool ok[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                  const int j = j0 + k * kProducerThreads;
+                  const int pp = j >> qshift;
+                  pos[k] = (j < items) ? pp : -1;
+                  const int r = (int)__umulhi((unsigned)pp, c.pitch_magic);
+                  const int xp = pp - r * c.pitch;
+                  const int y_in = c.sy * (y0 + r - c.lead_y) + phy;
                   const int x_in = c.sx * (xp - c.lead_x) + phx;
-                  const bool ok = row_ok && x_in >= 0 && x_in < Win;
-                  cp_async16_zfill(row_s + (uint32_t)xp * 16u, row_g + (size_t)(ok ? x_in : 0) * a.src_cs * 2, ok ? 16u : 0u);
+                  ok[k] = (j < items) && y_in >= 0 && y_in < Hin && x_in >= 0 && x_in < Win;
+                  raw[k] = make_uint4(0u, 0u, 0u, 0u);
+                  if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(plane + ((size_t)y_in * Win + x_in) * a.src_cs + ch0));
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                  if (pos[k] < 0) continue;
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (ok[k]) {
+                    o = xform8_h2(raw[k], s2, t2, l2);
+                  }
+                  *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
                 }
               }
             }
           }
-          cp_async_commit_group();
-          finish_pending(1);
-          pend_stage = stage;
-          pend_y0 = y0;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            ps2[e] = __floats2half2_rn(xs[ch0 + 2 * e], xs[ch0 + 2 * e + 1]);
-            pt2[e] = __floats2half2_rn(xh[ch0 + 2 * e], xh[ch0 + 2 * e + 1]);
-            pl2[e] = __floats2half2_rn(xl[ch0 + 2 * e], xl[ch0 + 2 * e + 1]);
-          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&full_bar[stage]);
           if (++stage == c.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-    finish_pending(0);
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // The whole warp runs the (uniform) control flow; lane 0 issues.  Per MMA: one 64-bit add on the A
