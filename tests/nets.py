@@ -25,6 +25,20 @@ STUDENT = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
                kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
 
 
+# the other BASELINE.json configurations, at their real patch sizes
+TEACHER = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
+               kw=M.plain_arch_kwargs([32, 64, 128, 256, 320, 320], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
+RESENC_M_STUDENT = dict(cls=M.RESENC, in_ch=4, heads=4, patch=(128, 128, 128),
+                        kw=M.resenc_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6,
+                                                [[1, 1, 1]] + [[2, 2, 2]] * 5, [1, 3, 4, 6, 6, 6]))
+# topology returned by the reference's get_pool_and_conv_props for spacing (2.0, 0.977, 0.977), patch (160, 96, 96)
+# (tests/golden/sliding_window_golden.json 'topology'[0]); 61 labels as in engine/config/fast_nnunet_bone_turbo.ini
+BONE_TURBO = dict(cls=M.PLAIN, in_ch=1, heads=61, patch=(160, 96, 96),
+                  kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160],
+                                         [[1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
+                                         [[1, 1, 1], [1, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2], [2, 1, 1]]))
+
+
 def make(spec, seed=1234, randomize_affine=True):
     sd = M.synthesize_state_dict(spec['cls'], spec['kw'], spec['in_ch'], spec['heads'], seed=seed,
                                  randomize_affine=randomize_affine)
