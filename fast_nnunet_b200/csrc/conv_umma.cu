@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     int buf = 0;
     uint32_t tphase0 = 0, tphase1 = 0;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
+    const bool do_stats = a.dst_stats != nullptr;
     const int Dout = a.out_d[0], Hout = a.out_d[1], Wout = a.out_d[2];
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const UnitIdx ui = decode_unit(p, u);
@@ -450,26 +451,31 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           uint32_t acc[16];
           tmem_ld16(d_base + (uint32_t)(i * c.Nc + n0), acc);
           if (valid) {
-            __half hv[16];
+            __half2 hv[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              hv[j] = __float2half_rn(__uint_as_float(acc[j]) + bias[j]);
-              const float f = __half2float(hv[j]);
-              s1[j] += f;
-              s2[j] = fmaf(f, f, s2[j]);
+            for (int j = 0; j < 16; j += 2) {
+              const float v0 = __uint_as_float(acc[j]) + bias[j];
+              const float v1 = __uint_as_float(acc[j + 1]) + bias[j + 1];
+              if (do_stats) {   // fp32 values: the fp16 rounding error averages out over the patch
+                s1[j] += v0;
+                s2[j] = fmaf(v0, v0, s2[j]);
+                s1[j + 1] += v1;
+                s2[j + 1] = fmaf(v1, v1, s2[j + 1]);
+              }
+              hv[j >> 1] = __floats2half2_rn(v0, v1);
             }
             __half* q = out_plane + ((size_t)(y * ys + oy_off) * Wout + (xo * xsn + ox_off)) * a.dst_cs + co0;
             if (vec_store && full16) {
               reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
-              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
+              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[4]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (co0 + j < a.cout) q[j] = hv[j];
+                if (co0 + j < a.cout) q[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
         }
-        if (a.dst_stats) {
+        if (do_stats) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
 #pragma unroll

@@ -368,25 +368,34 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
           tmem_ld16_nowait(t_c + (uint32_t)(2 * CP + g0), r2);
           tmem_wait_ld();
           if (col_ok) {
-            __half hv[16];
+            __half2 hv[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float bj;
-              if constexpr (CP == 16) bj = bias[j];
-              else bj = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
-              hv[j] = __float2half_rn((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]) + bj);
-              const float f = __half2float(hv[j]);
-              s1[g0 + j] += f;
-              s2[g0 + j] = fmaf(f, f, s2[g0 + j]);
+            for (int j = 0; j < 16; j += 2) {
+              float bj0, bj1;
+              if constexpr (CP == 16) {
+                bj0 = bias[j];
+                bj1 = bias[j + 1];
+              } else {
+                bj0 = (a.bias && g0 + j < a.cout) ? __ldg(a.bias + g0 + j) : 0.f;
+                bj1 = (a.bias && g0 + j + 1 < a.cout) ? __ldg(a.bias + g0 + j + 1) : 0.f;
+              }
+              const float v0 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]) + bj0;
+              const float v1 = (__uint_as_float(r0[j + 1]) + __uint_as_float(r1[j + 1])) + __uint_as_float(r2[j + 1]) + bj1;
+              // InstanceNorm partial sums on the fp32 values (the fp16 rounding error averages out over >= 1e5 voxels)
+              s1[g0 + j] += v0;
+              s2[g0 + j] = fmaf(v0, v0, s2[g0 + j]);
+              s1[g0 + j + 1] += v1;
+              s2[g0 + j + 1] = fmaf(v1, v1, s2[g0 + j + 1]);
+              hv[j >> 1] = __floats2half2_rn(v0, v1);
             }
             __half* q = out_px + g0;
             if (vec_store && g0 + 16 <= a.cout) {
               reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
-              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[8]);
+              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[4]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (g0 + j < a.cout) q[j] = hv[j];
+                if (g0 + j < a.cout) q[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
         }
