@@ -3,6 +3,10 @@
 // Reference semantics: distillation/nnunetv2/inference/predict_from_raw_data.py:541-631.
 // All kernels are HBM-bound; they use 128-bit accesses where the innermost start is 16-byte aligned
 // and grids sized in multiples of the SM count.
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.cuh"
 
 namespace fnnu {
@@ -51,6 +55,46 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(
   }
 }
 
+// Single-channel volumes (CT): one thread converts 8 consecutive z voxels -> one 16-byte store.
+// Mirrored-z copies read the 8 source voxels in reverse.  Requires pZ % 8 == 0 and cs == 1.
+__global__ void __launch_bounds__(256) gather_tiles_c1_vec8_kernel(
+    const float* __restrict__ vol, int X, int Y, int Z, const int32_t* __restrict__ starts, int n_tiles, int pX,
+    int pY, int pZ, FlipList flips, int n_flips, __half* __restrict__ out) {
+  const int zq = pZ >> 3;
+  const size_t per_sample = (size_t)pX * pY * zq;
+  const size_t total = per_sample * n_tiles * n_flips;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t n = i / per_sample;
+    size_t r = i - n * per_sample;
+    int z = (int)(r % zq) << 3;
+    int y = (int)((r / zq) % pY);
+    int x = (int)(r / ((size_t)zq * pY));
+    int t = (int)(n / n_flips);
+    int f = flips.m[n - (size_t)t * n_flips];
+    int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
+    int gx = sx + ((f & 1) ? pX - 1 - x : x);
+    int gy = sy + ((f & 2) ? pY - 1 - y : y);
+    const bool rz = (f & 4) != 0;
+    int gz = sz + (rz ? pZ - 8 - z : z);
+    const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
+    float v[8];
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      h[k] = rz ? __floats2half2_rn(v[7 - 2 * k], v[6 - 2 * k]) : __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(out + n * (size_t)pX * pY * pZ + ((size_t)x * pY + y) * pZ + z) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // accumulate: one launch per tile (tiles of a batch overlap, so they are applied in order).
 // ------------------------------------------------------------------------------------------------
@@ -70,13 +114,24 @@ __device__ __forceinline__ void acc_add<__half>(__half* p, float v) {
   *p = __float2half_rn(__fadd_rn(__half2float(*p), v));
 }
 
-// Generic path: any heads / stride / alignment.  One thread per tile voxel.
+// Tiles of one launch ("round"): mutually non-overlapping, so they can be applied concurrently; overlapping
+// tiles always sit in different rounds, in tile order, which keeps the per-voxel summation order of the reference.
+#define FNNU_ROUND_MAX 8
+struct TileRound {
+  int n;
+  int sx[FNNU_ROUND_MAX], sy[FNNU_ROUND_MAX], sz[FNNU_ROUND_MAX];
+  int idx[FNNU_ROUND_MAX];    // index of the tile inside the call's prediction batch
+};
+
+// Generic path: any heads / stride / alignment.  One thread per tile voxel; blockIdx.y = tile of the round.
 template <typename InT, typename AccT>
 __global__ void __launch_bounds__(256) accumulate_generic_kernel(
-    const InT* __restrict__ preds, int ps, int heads, int sx, int sy, int sz, int pX, int pY, int pZ,
+    const InT* __restrict__ preds_all, int ps, int heads, TileRound tr, int pX, int pY, int pZ,
     FlipList flips, int n_flips, const __half* __restrict__ gauss, AccT* __restrict__ acc, int X, int Y,
     int Z) {
   const size_t pvox = (size_t)pX * pY * pZ;
+  const int sx = tr.sx[blockIdx.y], sy = tr.sy[blockIdx.y], sz = tr.sz[blockIdx.y];
+  const InT* __restrict__ preds = preds_all + (size_t)tr.idx[blockIdx.y] * n_flips * pvox * ps;
   const size_t hstride = (size_t)X * Y * Z;
   const float inv_dummy = (float)n_flips;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pvox;
@@ -107,11 +162,13 @@ __global__ void __launch_bounds__(256) accumulate_generic_kernel(
 // Fast path: fp16 predictions, 2 heads stored as half2 per voxel, fp32 accumulators, pZ % 4 == 0,
 // (sz % 4 == 0 && Z % 4 == 0): one thread handles 4 consecutive z voxels with 128-bit accesses.
 __global__ void __launch_bounds__(256) accumulate_h2_vec4_kernel(
-    const __half* __restrict__ preds, int sx, int sy, int sz, int pX, int pY, int pZ, FlipList flips,
+    const __half* __restrict__ preds_all, TileRound tr, int pX, int pY, int pZ, FlipList flips,
     int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
   const int zq = pZ >> 2;
   const size_t nthreads = (size_t)pX * pY * zq;
   const size_t pvox = (size_t)pX * pY * pZ;
+  const int sx = tr.sx[blockIdx.y], sy = tr.sy[blockIdx.y], sz = tr.sz[blockIdx.y];
+  const __half* __restrict__ preds = preds_all + (size_t)tr.idx[blockIdx.y] * n_flips * pvox * 2;
   const size_t hstride = (size_t)X * Y * Z;
   const float nf = (float)n_flips;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads;
@@ -328,6 +385,13 @@ extern "C" int fnnu_gather_tiles(const float* volume, int channels, const int vo
   FlipList fl;
   for (int i = 0; i < 8; ++i) fl.m[i] = i < n_flips ? (flip_masks[i] & 7) : 0;
   size_t total = (size_t)patch[0] * patch[1] * patch[2] * n_tiles * n_flips;
+  if (channels == 1 && c_stride == 1 && patch[2] % 8 == 0 && ((uintptr_t)out % 16) == 0) {
+    gather_tiles_c1_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        volume, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1], patch[2], fl, n_flips,
+        (__half*)out);
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
   gather_tiles_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       volume, channels, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1],
       patch[2], fl, n_flips, (__half*)out, c_stride);
@@ -349,37 +413,62 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
   const int pX = patch[0], pY = patch[1], pZ = patch[2];
   const int X = vol_dims[0], Y = vol_dims[1], Z = vol_dims[2];
   const size_t pvox = (size_t)pX * pY * pZ;
-  const size_t esz = in_dtype == FNNU_IN_F16 ? 2 : 4;
   cudaStream_t s = (cudaStream_t)stream;
+  bool vec = in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32 && heads == 2 && p_stride == 2 && (pZ % 4 == 0) &&
+             (Z % 4 == 0) && (((uintptr_t)preds) % 16 == 0) && (((uintptr_t)acc) % 16 == 0) &&
+             (!gaussian || ((uintptr_t)gaussian) % 8 == 0);
   for (int t = 0; t < n_tiles; ++t) {
     int sx = starts_host[t * 3 + 0], sy = starts_host[t * 3 + 1], sz = starts_host[t * 3 + 2];
     FNNU_CHECK_ARG(sx >= 0 && sy >= 0 && sz >= 0 && sx + pX <= X && sy + pY <= Y && sz + pZ <= Z,
                    "accumulate: tile %d (%d,%d,%d) outside the volume", t, sx, sy, sz);
-    const char* p = (const char*)preds + (size_t)t * n_flips * pvox * p_stride * esz;
-    bool vec = in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32 && heads == 2 && p_stride == 2 &&
-               (pZ % 4 == 0) && (sz % 4 == 0) && (Z % 4 == 0) && (((uintptr_t)p) % 16 == 0) &&
-               (((uintptr_t)acc) % 16 == 0) && (!gaussian || ((uintptr_t)gaussian) % 8 == 0);
-    if (vec) {
-      accumulate_h2_vec4_kernel<<<grid_for(pvox / 4, 256), 256, 0, s>>>(
-          (const __half*)p, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian, (float*)acc, X, Y, Z);
-    } else if (in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32) {
-      accumulate_generic_kernel<__half, float><<<grid_for(pvox, 256), 256, 0, s>>>(
-          (const __half*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
-          (float*)acc, X, Y, Z);
-    } else if (in_dtype == FNNU_IN_F16) {
-      accumulate_generic_kernel<__half, __half><<<grid_for(pvox, 256), 256, 0, s>>>(
-          (const __half*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
-          (__half*)acc, X, Y, Z);
-    } else if (acc_dtype == FNNU_ACC_F32) {
-      accumulate_generic_kernel<float, float><<<grid_for(pvox, 256), 256, 0, s>>>(
-          (const float*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
-          (float*)acc, X, Y, Z);
-    } else {
-      accumulate_generic_kernel<float, __half><<<grid_for(pvox, 256), 256, 0, s>>>(
-          (const float*)p, p_stride, heads, sx, sy, sz, pX, pY, pZ, fl, n_flips, (const __half*)gaussian,
-          (__half*)acc, X, Y, Z);
+    if (sz % 4 != 0) vec = false;
+  }
+  // rounds: round[t] = 1 + max round of the earlier tiles that overlap t (0 if none)
+  std::vector<int> round(n_tiles, 0);
+  int n_rounds = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    for (int u = 0; u < t; ++u) {
+      bool ov = abs(starts_host[t * 3] - starts_host[u * 3]) < pX && abs(starts_host[t * 3 + 1] - starts_host[u * 3 + 1]) < pY &&
+                abs(starts_host[t * 3 + 2] - starts_host[u * 3 + 2]) < pZ;
+      if (ov && round[u] + 1 > round[t]) round[t] = round[u] + 1;
     }
-    FNNU_LAUNCH_CHECK();
+    if (round[t] + 1 > n_rounds) n_rounds = round[t] + 1;
+  }
+  for (int r = 0; r < n_rounds; ++r) {
+    int t = 0;
+    while (t < n_tiles) {
+      TileRound tr;
+      tr.n = 0;
+      for (; t < n_tiles && tr.n < FNNU_ROUND_MAX; ++t) {
+        if (round[t] != r) continue;
+        tr.sx[tr.n] = starts_host[t * 3];
+        tr.sy[tr.n] = starts_host[t * 3 + 1];
+        tr.sz[tr.n] = starts_host[t * 3 + 2];
+        tr.idx[tr.n] = t;
+        ++tr.n;
+      }
+      if (tr.n == 0) break;
+      if (vec) {
+        dim3 grid((unsigned)grid_for(pvox / 4, 256, 16 / (tr.n > 4 ? 4 : tr.n) + 1), (unsigned)tr.n);
+        accumulate_h2_vec4_kernel<<<grid, 256, 0, s>>>((const __half*)preds, tr, pX, pY, pZ, fl, n_flips,
+                                                       (const __half*)gaussian, (float*)acc, X, Y, Z);
+      } else {
+        dim3 grid((unsigned)grid_for(pvox, 256), (unsigned)tr.n);
+        if (in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32)
+          accumulate_generic_kernel<__half, float><<<grid, 256, 0, s>>>((const __half*)preds, p_stride, heads, tr, pX, pY, pZ, fl,
+                                                                        n_flips, (const __half*)gaussian, (float*)acc, X, Y, Z);
+        else if (in_dtype == FNNU_IN_F16)
+          accumulate_generic_kernel<__half, __half><<<grid, 256, 0, s>>>((const __half*)preds, p_stride, heads, tr, pX, pY, pZ, fl,
+                                                                         n_flips, (const __half*)gaussian, (__half*)acc, X, Y, Z);
+        else if (acc_dtype == FNNU_ACC_F32)
+          accumulate_generic_kernel<float, float><<<grid, 256, 0, s>>>((const float*)preds, p_stride, heads, tr, pX, pY, pZ, fl,
+                                                                       n_flips, (const __half*)gaussian, (float*)acc, X, Y, Z);
+        else
+          accumulate_generic_kernel<float, __half><<<grid, 256, 0, s>>>((const float*)preds, p_stride, heads, tr, pX, pY, pZ, fl,
+                                                                        n_flips, (const __half*)gaussian, (__half*)acc, X, Y, Z);
+      }
+      FNNU_LAUNCH_CHECK();
+    }
   }
   return FNNU_OK;
 }

@@ -312,8 +312,21 @@ class nnUNetPredictor(object):
             self._mark('accumulate')
             E.accumulate_tiles(out_ptr, _lib.IN_F16, out_cs, heads, local[i:i + n], patch, flips, gauss, acc)
             self._mark(None)
-            launches += 1 + eng.launch_counts()[0] + n
+            launches += 1 + eng.launch_counts()[0] + self._accumulate_rounds(local[i:i + n], patch)
         self.last_launches += launches
+
+    @staticmethod
+    def _accumulate_rounds(starts, patch) -> int:
+        """Number of kernels fnnu_accumulate_tiles launches for these tiles: tiles are applied in rounds of mutually
+        non-overlapping tiles (round = 1 + max round of the earlier overlapping tiles), at most 8 tiles per launch."""
+        rounds = []
+        for t, s in enumerate(starts):
+            r = 0
+            for u in range(t):
+                if all(abs(int(s[a]) - int(starts[u][a])) < patch[a] for a in range(3)):
+                    r = max(r, rounds[u] + 1)
+            rounds.append(r)
+        return sum((rounds.count(r) + 7) // 8 for r in set(rounds))
 
     # ------------------------------------------------------------------ phase timing (bench only)
     def _mark(self, phase):
