@@ -33,6 +33,8 @@ struct RowsCfg {
   int slots;              // TMEM tile slots (Nf columns each)
   int n_yseg, seg_rows;
   int smem_bytes;
+  int occ;                // CTAs per SM this launch is planned for (1 or 2): halves smem / TMEM budgets
+  int tmem_cols;
 };
 
 struct RowsArgs {
@@ -73,10 +75,18 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   c.w_bytes = c.nkz * c.nkx * c.chunks * 2 * c.Nf * 16;
   if (c.w_bytes > 80 * 1024) return false;
   const int misc = 1024 + 3 * a.cin * 4 + 1024;
-  int st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
-  if (st < 4) return false;
+  // Two CTAs per SM when both fit (256 TMEM columns and ~113 KB of shared memory each): the kernel is
+  // latency-bound per warp (ncu: issue active 45 %, tc pipe 42 %), so a second resident CTA fills the bubbles.
+  c.occ = 2;
+  int st = (kRowsSmemLimit / 2 - misc - c.w_bytes) / c.stage_bytes;
+  if (st < 3 || 256 / c.Nf < 4) {
+    c.occ = 1;
+    st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
+  }
+  if (st < 3) return false;
   c.stages = st > kRowsMaxStages ? kRowsMaxStages : st;
-  c.slots = 512 / c.Nf;
+  c.tmem_cols = c.occ == 2 ? 256 : 512;
+  c.slots = c.tmem_cols / c.Nf;
   if (c.slots > kRowsMaxSlots) c.slots = kRowsMaxSlots;
   if (c.slots < 4) return false;
   c.smem_bytes = c.w_bytes + c.stages * c.stage_bytes + misc;
@@ -88,8 +98,8 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   return true;
 }
 
-template <int CP, int CHUNKS>   // cout_pad (16 | 32) sizes the per-thread InstanceNorm partials; CHUNKS = Cin / 16
-__global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const __grid_constant__ RowsArgs p) {
+template <int CP, int CHUNKS, int OCC>   // cout_pad (16 | 32); CHUNKS = Cin / 16; OCC = CTAs per SM
+__global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const __grid_constant__ RowsArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const RowsCfg& c = p.c;
   const ConvArgs& a = p.a;
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kRowsMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)c.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_umma_rows_kernel(const _
   __syncthreads();
   if (warp == kRowsMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)c.tmem_cols));
   }
 }
 
@@ -463,21 +473,23 @@ int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
     return FNNU_E_UNSUPPORTED;
   }
   p.n_units = a.batch * p.c.D * p.c.n_yseg;
-  int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-#define FNNU_ROWS_CASE(CPV, CHV)                                                                                    \
-  if (a.cout_pad == CPV && p.c.chunks == CHV) {                                                                      \
+  int grid = p.n_units < num_sms() * p.c.occ ? p.n_units : num_sms() * p.c.occ;
+#define FNNU_ROWS_CASE(CPV, CHV, OCCV)                                                                                    \
+  if (a.cout_pad == CPV && p.c.chunks == CHV && p.c.occ == OCCV) {                                                                 \
     static bool attr_set = false;                                                                                    \
     if (!attr_set) {                                                                                                 \
-      FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<CPV, CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+      FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<CPV, CHV, OCCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                      kRowsSmemLimit));                                                               \
       attr_set = true;                                                                                               \
     }                                                                                                                \
-    conv_umma_rows_kernel<CPV, CHV><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);                                   \
+    conv_umma_rows_kernel<CPV, CHV, OCCV><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);                                   \
   }
-  FNNU_ROWS_CASE(16, 1)
-  else FNNU_ROWS_CASE(16, 2)
-  else FNNU_ROWS_CASE(32, 1)
-  else FNNU_ROWS_CASE(32, 2)
+  FNNU_ROWS_CASE(16, 1, 2)
+  else FNNU_ROWS_CASE(16, 2, 2)
+  else FNNU_ROWS_CASE(16, 1, 1)
+  else FNNU_ROWS_CASE(16, 2, 1)
+  else FNNU_ROWS_CASE(32, 1, 1)
+  else FNNU_ROWS_CASE(32, 2, 1)
   else {
     set_error("conv_umma_rows: no instantiation for cout_pad=%d chunks=%d", a.cout_pad, p.c.chunks);
     return FNNU_E_UNSUPPORTED;
