@@ -79,11 +79,12 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   // latency-bound per warp (ncu: issue active 45 %, tc pipe 42 %), so a second resident CTA fills the bubbles.
   c.occ = 2;
   int st = (kRowsSmemLimit / 2 - misc - c.w_bytes) / c.stage_bytes;
-  if (st < 3 || 256 / c.Nf < 4) {
+  // stages > producer groups is required: a group publishes row r only while it prefetches row r + 4
+  if (st <= kRowsProducerGroups || 256 / c.Nf < 4) {
     c.occ = 1;
     st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
   }
-  if (st < 3) return false;
+  if (st <= kRowsProducerGroups) return false;
   c.stages = st > kRowsMaxStages ? kRowsMaxStages : st;
   c.tmem_cols = c.occ == 2 ? 256 : 512;
   c.slots = c.tmem_cols / c.Nf;
