@@ -75,10 +75,12 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   c.w_bytes = c.nkz * c.nkx * c.chunks * 2 * c.Nf * 16;
   if (c.w_bytes > 80 * 1024) return false;
   const int misc = 1024 + 3 * a.cin * 4 + 1024;
-  // Two CTAs per SM when both fit (256 TMEM columns and ~113 KB of shared memory each): the kernel is
-  // latency-bound per warp (ncu: issue active 45 %, tc pipe 42 %), so a second resident CTA fills the bubbles.
+  // Two CTAs per SM (256 TMEM columns and ~113 KB of shared memory each) were measured SLOWER (enc0.1: 2.8 -> 4.0 ms
+  // per 32 patches): the kernel is bound by shared-memory traffic (A is re-read for each of the 9 taps), not by
+  // latency, so the variant stays compiled but is not selected.
   c.occ = 2;
-  int st = (kRowsSmemLimit / 2 - misc - c.w_bytes) / c.stage_bytes;
+  if (true) c.occ = 1;
+  int st = (kRowsSmemLimit / c.occ - misc - c.w_bytes) / c.stage_bytes;
   // stages > producer groups is required: a group publishes row r only while it prefetches row r + 4
   if (st <= kRowsProducerGroups || 256 / c.Nf < 4) {
     c.occ = 1;
