@@ -201,13 +201,18 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
 #pragma unroll
         for (int kz = 0; kz < 3; ++kz) {
           if (!((pend_mask >> kz) & 1)) continue;
+          // all loads, then all math, then all stores: the in-place update would otherwise serialise on
+          // possible aliasing between one item's store and the next item's load
+          uint4 v[N_IT];
 #pragma unroll
-          for (int it = 0; it < N_IT; ++it) {
-            if ((inimg >> it) & 1) {
-              uint4* ptr = reinterpret_cast<uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16));
-              *ptr = xform8_h2(*ptr, s2, t2, l2);
-            }
-          }
+          for (int it = 0; it < N_IT; ++it)
+            if ((inimg >> it) & 1) v[it] = *reinterpret_cast<const uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16));
+#pragma unroll
+          for (int it = 0; it < N_IT; ++it)
+            if ((inimg >> it) & 1) v[it] = xform8_h2(v[it], s2, t2, l2);
+#pragma unroll
+          for (int it = 0; it < N_IT; ++it)
+            if ((inimg >> it) & 1) *reinterpret_cast<uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16)) = v[it];
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
