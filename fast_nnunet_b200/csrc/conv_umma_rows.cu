@@ -10,7 +10,7 @@
 //   out[y][x, co] = D'[y - 1][x, (2, co)] + D'[y][x, (1, co)] + D'[y + 1][x, (0, co)]
 // is a sum of three accumulator tiles AT THE SAME LANE, done by the epilogue while it drains TMEM — no
 // cross-lane traffic.  Because an input row now feeds exactly one accumulator tile, the kernel streams:
-//   producers (4 groups x 2 warps): one smem stage = one input row x 3 z-planes x Cin, normalise-on-load
+//   producers (16 warps in 8 or 4 groups): one smem stage = one input row x 3 z-planes x Cin, normalise-on-load
 //   MMA warp: 9 * Cin/16 MMAs per stage into a ring of TMEM tile slots, commit per row
 //   epilogue (4 warps): output row y as soon as tile y+1 is complete; frees tile y-1
 // Weights (all 27 taps) stay resident in shared memory for the whole kernel (<= 64 KB).
@@ -43,12 +43,16 @@ struct RowsArgs {
   int n_units;
 };
 
-constexpr int kRowsProducerGroups = 4;
-constexpr int kRowsGroupThreads = 64;
-constexpr int kRowsProducerThreads = kRowsProducerGroups * kRowsGroupThreads;   // warps 0-7
-constexpr int kRowsEpiWarp0 = 8;                                                // warps 8-11
-constexpr int kRowsMmaWarp = 12;
-constexpr int kRowsThreads = 13 * 32;
+// 16 producer warps (the producers are latency-bound: ncu shows them busy ~85 % at one instruction per ~8 cycles
+// per warp), dealt in groups of 64 * CHUNKS threads (8 groups for Cin 16, 4 groups for Cin 32) so that a thread
+// always covers a row in 5 steps of 32 positions.  Warps 16-19: epilogue, warp 20: MMA.
+constexpr int kRowsProducerWarps = 16;
+constexpr int kRowsProducerThreads = kRowsProducerWarps * 32;
+constexpr int kRowsMmaWarp = kRowsProducerWarps + 4;
+constexpr int kRowsThreads = 24 * 32;   // 6 warpgroups: 4 producer, 1 epilogue, 1 holding the MMA warp (+3 idle warps)
+constexpr int kRegsProducer = 72, kRegsMma = 40, kRegsEpilogue = 152;   // setmaxnreg: 512 x 72 + 128 x 40 + 128 x 152 = 768 x 80
+__host__ __device__ constexpr int rows_group_threads(int chunks) { return 64 * chunks; }
+__host__ __device__ constexpr int rows_groups(int chunks) { return kRowsProducerThreads / (64 * chunks); }
 constexpr int kRowsMaxStages = 16;
 constexpr int kRowsMaxSlots = 10;
 constexpr int kRowsSmemLimit = 227 * 1024;
@@ -82,11 +86,11 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   if (true) c.occ = 1;
   int st = (kRowsSmemLimit / c.occ - misc - c.w_bytes) / c.stage_bytes;
   // stages > producer groups is required: a group publishes row r only while it prefetches row r + 4
-  if (st <= kRowsProducerGroups || 256 / c.Nf < 4) {
+  if (st <= rows_groups(c.chunks) || 256 / c.Nf < 4) {
     c.occ = 1;
     st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
   }
-  if (st <= kRowsProducerGroups) return false;
+  if (st <= rows_groups(c.chunks)) return false;
   c.stages = st > kRowsMaxStages ? kRowsMaxStages : st;
   c.tmem_cols = c.occ == 2 ? 256 : 512;
   c.slots = c.tmem_cols / c.Nf;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
-      mbar_init(&full_bar[s], kRowsGroupThreads);
+      mbar_init(&full_bar[s], rows_group_threads(CHUNKS));
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < c.slots; ++s) {
@@ -158,18 +162,21 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     if (yb > c.H) yb = c.H;
   };
 
-  if (warp < 8) {
+  if (warp < kRowsProducerWarps) {
     // =========================== PRODUCERS ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     const int tid = threadIdx.x;
-    const int grp = tid / kRowsGroupThreads;          // stages are dealt round-robin to the 4 groups
-    const int gt = tid - grp * kRowsGroupThreads;
+    constexpr int kGroupThreads = rows_group_threads(CHUNKS);
+    constexpr int kGroups = rows_groups(CHUNKS);
+    const int grp = tid / kGroupThreads;              // stages are dealt round-robin to the groups
+    const int gt = tid - grp * kGroupThreads;
     // A thread owns ONE 8-channel group q (its scale/shift/slope live in registers) and every XP_STEP-th
     // position of a row; consecutive lanes fetch the consecutive 16-byte pieces of whole voxels.  Everything
     // that does not depend on the row (offsets, in-image flags) is computed once, so the per-row loop is
     // one cp.async per item and, one stage later, LDS.128 + 12 half2 ops + STS.128 per item.
     constexpr int kQ_ = 2 * CHUNKS;
-    constexpr int XP_STEP = kRowsGroupThreads / kQ_;          // 32 (Cin 16) or 16 (Cin 32)
-    constexpr int N_IT = (140 + XP_STEP - 1) / XP_STEP;       // 5 or 9
+    constexpr int XP_STEP = kGroupThreads / kQ_;              // 32 positions per step
+    constexpr int N_IT = (140 + XP_STEP - 1) / XP_STEP;       // 5
     const int q = gt & (kQ_ - 1);
     const int xp0 = gt / kQ_;
     uint32_t goff[N_IT];                                      // byte offset of the voxel within its row
@@ -201,18 +208,13 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
 #pragma unroll
         for (int kz = 0; kz < 3; ++kz) {
           if (!((pend_mask >> kz) & 1)) continue;
-          // all loads, then all math, then all stores: the in-place update would otherwise serialise on
-          // possible aliasing between one item's store and the next item's load
-          uint4 v[N_IT];
 #pragma unroll
-          for (int it = 0; it < N_IT; ++it)
-            if ((inimg >> it) & 1) v[it] = *reinterpret_cast<const uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16));
-#pragma unroll
-          for (int it = 0; it < N_IT; ++it)
-            if ((inimg >> it) & 1) v[it] = xform8_h2(v[it], s2, t2, l2);
-#pragma unroll
-          for (int it = 0; it < N_IT; ++it)
-            if ((inimg >> it) & 1) *reinterpret_cast<uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16)) = v[it];
+          for (int it = 0; it < N_IT; ++it) {
+            if ((inimg >> it) & 1) {
+              uint4* ptr = reinterpret_cast<uint4*>(st + kz * plane_bytes + it * (XP_STEP * 16));
+              *ptr = xform8_h2(*ptr, s2, t2, l2);
+            }
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
       const int n_rows = (yb - ya) + 2;
       const char* plane0 = reinterpret_cast<const char*>(a.src) + (((size_t)b * c.D + (z - c.pz)) * c.H) * row_bytes;
       for (int j = 0; j < n_rows; ++j, ++row_counter) {
-        if ((int)(row_counter & (kRowsProducerGroups - 1)) != grp) continue;
+        if ((int)(row_counter & (kGroups - 1)) != grp) continue;
         const int stage = (int)(row_counter % c.stages);
         const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -273,8 +275,10 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
       }
     }
     finish_pending(0);
-  } else if (warp == kRowsMmaWarp) {
-    // =========================== MMA ISSUER ===========================
+  } else if (warp >= kRowsMmaWarp) {
+    // =========================== MMA ISSUER (warp 20; warps 21-23 only donate registers) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+    if (warp == kRowsMmaWarp) {
     // One elected lane issues; every descriptor offset of a row's 9 * CHUNKS MMAs is a compile-time constant
     // added to the stage base, so the issue path is ~a dozen instructions per MMA (the MMA itself occupies the
     // tensor pipe for ~64 cycles of operand fetch).
@@ -327,8 +331,10 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         if (++slot == c.slots) { slot = 0; sphase ^= 1; }
       }
     }
+    }
   } else {
     // =========================== EPILOGUE ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int wq = warp & 3;
     const int x = wq * 32 + lane;                   // output column == TMEM lane
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
