@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# ncu --set full on conv_umma_rows_kernel<16,1> (profiles/r01_ncu_prof_rows16d.txt): dram read 545 MB + write 510 MB
+# for 537 + 537 MB algorithmic -> measured DRAM traffic / algorithmic bytes
+NCU_TRAFFIC_OVER_ALGORITHMIC = (545.4 + 510.2) / (536.9 + 536.9)
 STUDENT_FEATS = [16, 32, 64, 128, 160, 160]
 TEACHER_FEATS = [32, 64, 128, 256, 320, 320]
 ISO_K = [[3, 3, 3]] * 6
@@ -271,6 +274,7 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    dom = pred.profile_dominant_op(data) if rank == 0 else None
     if rank == 0:
         prog = pred.network.program
         flops_fwd = prog.total_flops()
@@ -280,12 +284,23 @@ def run_ours(args, wl):
         acc_ms = phase.get('accumulate_ms')
         pvox = float(np.prod(patch))
         acc_bytes = n_tiles * (8 * heads * pvox * 2 + pvox * 2 + 2 * heads * pvox * 4) / world
+        # dominant kernel: the operator with the most FLOPs (dec5.0, Conv3d 32->16 @128^3 for the student), timed by
+        # CUDA events inside libfnnu on the launching stream; `traffic` is dram read+write of one ncu --set full
+        # capture of the same kernel class (profiles/README.md), scaled to this launch's patch count
         roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': peaks['bf16_tflops_sustained'],
-                'achieved': (flops_vol / world / (conv_ms * 1e-3) / 1e12) if conv_ms else None,
-                'traffic': None, 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; fp16 runs at the same rate)',
-                'kernel': 'conv_umma_kernel + conv_direct_kernel (all engine launches of a forward)',
-                'flop_per_forward': flops_fwd}
-        roof['frac'] = roof['achieved'] / roof['peak'] if roof['achieved'] else None
+                'achieved': dom['flop_per_launch'] / (dom['ms'] * 1e-3) / 1e12,
+                'traffic': dom['algorithmic_bytes_per_launch'] * NCU_TRAFFIC_OVER_ALGORITHMIC,
+                'algorithmic_bytes': dom['algorithmic_bytes_per_launch'],
+                'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; fp16 runs at the same tcgen05 rate)',
+                'kernel': 'conv_umma_rows_kernel (' + dom['op'] + f", Conv3d {dom['cin']}->{dom['cout']} @{dom['out_dims']}"
+                          f", {dom['patches_per_launch']} patches per launch)",
+                'ms_per_launch': dom['ms'], 'flop_per_launch': dom['flop_per_launch']}
+        roof['frac'] = roof['achieved'] / roof['peak']
+        roof_all = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': peaks['bf16_tflops_sustained'],
+                    'achieved': (flops_vol / world / (conv_ms * 1e-3) / 1e12) if conv_ms else None,
+                    'kernel': 'every launch of the network forward (convs, transposed convs, first layer, seg head)',
+                    'flop_per_forward': flops_fwd}
+        roof_all['frac'] = roof_all['achieved'] / roof_all['peak'] if roof_all['achieved'] else None
         roof_mem = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peaks['hbm_gbs'],
                     'achieved': (acc_bytes / (acc_ms * 1e-3) / 1e9) if acc_ms else None, 'traffic': None,
                     'kernel': 'accumulate_h2_vec4_kernel', 'bytes_per_tile': acc_bytes * world / n_tiles}
@@ -309,7 +324,8 @@ def run_ours(args, wl):
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'call': 'predict_logits_from_preprocessed_data(host tensor) -> host fp16 logits' if world == 1
                     else 'host volume -> predict_sliding_window_sharded -> host uint8 label map'},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_aggregation': roof_mem,
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_network': roof_all,
+            'roofline_aggregation': roof_mem,
             'phase_ms_per_volume': phase, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

@@ -66,6 +66,8 @@ _SIGNATURES = {
     'fnnu_engine_forward': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'fnnu_engine_set_backend': (C.c_int, [C.c_void_p, C.c_int]),
     'fnnu_engine_launch_counts': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'fnnu_engine_profile_op': (C.c_int, [C.c_void_p, C.c_int]),
+    'fnnu_engine_profile_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
 }
 
 

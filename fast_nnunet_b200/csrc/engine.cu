@@ -49,6 +49,9 @@ struct fnnu_engine {
   double* stats_base;
   size_t stats_bytes;
   int last_total, last_umma;
+  int profile_op = -1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
 };
 
 namespace {
@@ -352,7 +355,31 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
   return FNNU_OK;
 }
 
-extern "C" void fnnu_engine_destroy(fnnu_engine* e) { delete e; }
+extern "C" void fnnu_engine_destroy(fnnu_engine* e) {
+  if (!e) return;
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+}
+
+extern "C" int fnnu_engine_profile_op(fnnu_engine* e, int op_index) {
+  FNNU_CHECK_ARG(e && op_index < (int)e->ops.size(), "profile_op: index %d", op_index);
+  if (op_index >= 0 && !e->ev0) {
+    FNNU_CUDA(cudaEventCreate(&e->ev0));
+    FNNU_CUDA(cudaEventCreate(&e->ev1));
+  }
+  e->profile_op = op_index;
+  e->ev_valid = false;
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_engine_profile_ms(fnnu_engine* e, float* ms) {
+  FNNU_CHECK_ARG(e && ms, "profile_ms: null pointer");
+  FNNU_CHECK_ARG(e->ev_valid, "profile_ms: no profiled forward has run");
+  FNNU_CUDA(cudaEventSynchronize(e->ev1));
+  FNNU_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return FNNU_OK;
+}
 
 extern "C" void* fnnu_engine_buffer(fnnu_engine* e, int index) {
   if (!e || index < 0 || index >= (int)e->bufs.size()) return nullptr;
@@ -386,6 +413,8 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
   for (size_t i = 0; i < e->ops.size(); ++i) {
     Op& op = e->ops[i];
     int rc = FNNU_OK;
+    const bool prof = (int)i == e->profile_op;
+    if (prof) FNNU_CUDA(cudaEventRecord(e->ev0, s));
     if (op.kind == FNNU_OP_CONV || op.kind == FNNU_OP_TCONV) {
       op.conv.batch = batch;
       if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
@@ -404,6 +433,10 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
       rc = launch_avgpool(op.elt, s);
     }
     if (rc) return rc;
+    if (prof) {
+      FNNU_CUDA(cudaEventRecord(e->ev1, s));
+      e->ev_valid = true;
+    }
     ++total;
   }
   e->last_total = total;

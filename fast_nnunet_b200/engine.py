@@ -103,6 +103,14 @@ class NetworkEngine:
     def forward(self, batch: int):
         _lib.check(self.lib.fnnu_engine_forward(self.handle, int(batch), _lib.stream_ptr()))
 
+    def profile_op(self, index: int):
+        _lib.check(self.lib.fnnu_engine_profile_op(self.handle, int(index)))
+
+    def profile_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(self.lib.fnnu_engine_profile_ms(self.handle, C.byref(ms)))
+        return ms.value
+
     def launch_counts(self):
         t, u = C.c_int(0), C.c_int(0)
         _lib.check(self.lib.fnnu_engine_launch_counts(self.handle, C.byref(t), C.byref(u)))

@@ -328,6 +328,35 @@ class nnUNetPredictor(object):
             rounds.append(r)
         return sum((rounds.count(r) + 7) // 8 for r in set(rounds))
 
+    @torch.inference_mode()
+    def profile_dominant_op(self, data: torch.Tensor, n_batches: int = 6):
+        """bench.py: device time (CUDA events on the launching stream, inside libfnnu) of the network operator
+        with the most FLOPs, over `n_batches` real tile batches of `data`."""
+        patch = tuple(self.configuration_manager.patch_size)
+        flips = self._flip_masks()
+        nf = len(flips)
+        starts = sw.tile_starts(tuple(data.shape[1:]), patch, self.tile_step_size)
+        tpb = self._choose_tiles_per_batch(nf, len(starts))
+        eng = self.network.engine(self.device, tpb * nf)
+        prog = eng.program
+        flops = [o.flops(prog.buffers[o.src][0], prog.buffers[o.dst][0]) for o in prog.ops]
+        idx = int(np.argmax(flops))
+        eng.profile_op(idx)
+        starts_dev = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.int32)).to(self.device)
+        times = []
+        for k in range(min(n_batches, len(starts) // tpb)):
+            E.gather_tiles(data, starts_dev[k * tpb:(k + 1) * tpb], tpb, patch, flips, eng.buffer_ptr(prog.input_buffer),
+                           prog.buffers[prog.input_buffer][1])
+            eng.forward(tpb * nf)
+            times.append(eng.profile_ms())
+        eng.profile_op(-1)
+        op = prog.ops[idx]
+        in_d, out_d = prog.buffers[op.src][0], prog.buffers[op.dst][0]
+        n = tpb * nf
+        return {'op': op.name, 'cin': op.cin, 'cout': op.cout, 'out_dims': list(out_d), 'patches_per_launch': n,
+                'flop_per_launch': flops[idx] * n, 'ms': float(np.mean(times)), 'ms_all': [float(t) for t in times],
+                'algorithmic_bytes_per_launch': float(n * 2 * (np.prod(in_d) * op.cin + np.prod(out_d) * op.cout))}
+
     # ------------------------------------------------------------------ phase timing (bench only)
     def _mark(self, phase):
         """Closes the running phase and opens `phase` with CUDA events on the launching stream."""

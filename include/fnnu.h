@@ -154,6 +154,12 @@ int fnnu_engine_set_backend(fnnu_engine* e, int backend);
 /* Number of kernels the last fnnu_engine_forward launched, and how many of them were tcgen05. */
 int fnnu_engine_launch_counts(fnnu_engine* e, int* total, int* umma);
 
+/* Measurement hook (bench.py): fnnu_engine_profile_op(e, i) makes every following fnnu_engine_forward bracket
+ * operator i with two CUDA events on the launching stream (i < 0 switches it off); fnnu_engine_profile_ms
+ * synchronises on the second event and returns the device time of that operator in the LAST forward. */
+int fnnu_engine_profile_op(fnnu_engine* e, int op_index);
+int fnnu_engine_profile_ms(fnnu_engine* e, float* ms);
+
 /* Device pointer of the InstanceNorm sums of buffer `index`: double [max_batch][channels][2]
  * (sum, sum of squares of the stored fp16 values), valid after fnnu_engine_forward. */
 double* fnnu_engine_stats(fnnu_engine* e, int index);
