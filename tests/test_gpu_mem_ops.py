@@ -69,7 +69,8 @@ def test_accumulate_fp16_emulation_bit_exact(vol, patch, heads):
 
 @pytest.mark.parametrize('vol,patch,heads,pstride', [((64, 48, 64), (32, 32, 32), 2, 2), ((40, 48, 36), (32, 32, 32), 2, 2),
                                                      ((33, 35, 41), (16, 24, 20), 3, 8), ((48, 32, 32), (32, 32, 32), 61, 64)])
-def test_accumulate_tta_fp32(vol, patch, heads, pstride):
+@pytest.mark.parametrize('chunk', [0, 4, 7])
+def test_accumulate_tta_fp32(vol, patch, heads, pstride, chunk):
     """fp16 predictions of 8 mirrored passes -> un-flip, mean, Gaussian weight, fp32 accumulate, normalise."""
     starts = sw.tile_starts(vol, patch, 0.5)
     n = len(starts)
@@ -77,7 +78,13 @@ def test_accumulate_tta_fp32(vol, patch, heads, pstride):
     raw = (torch.randn((n * 8, *patch, pstride), generator=g) * 2).half().to(DEV)
     g16 = torch.from_numpy(sw.compute_gaussian(patch, 1. / 8, 10, np.float16)).to(DEV)
     acc = torch.zeros((heads, *vol), dtype=torch.float32, device=DEV)
-    E.accumulate_tiles(raw.data_ptr(), _lib.IN_F16, pstride, heads, starts, patch, FLIPS8, g16, acc)
+    # chunk = 0: all tiles in one call; otherwise batches of `chunk` tiles as the predictor issues them (batches of
+    # <= 8 tiles with 2 heads take the whole-batch kernel, everything else rounds of non-overlapping tiles)
+    step = chunk if chunk else n
+    per_tile = raw.shape[1] * raw.shape[2] * raw.shape[3] * pstride * 8 * 2
+    for i in range(0, n, step):
+        E.accumulate_tiles(raw.data_ptr() + i * per_tile, _lib.IN_F16, pstride, heads, starts[i:i + step], patch, FLIPS8,
+                           g16, acc)
     wsum = torch.empty(vol, dtype=torch.float32, device=DEV)
     E.weight_sum(sw.compute_steps_for_sliding_window(vol, patch, 0.5), patch, g16, wsum)
     # reference arithmetic in fp32 on the GPU with torch ops
