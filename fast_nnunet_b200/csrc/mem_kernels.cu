@@ -232,90 +232,6 @@ __global__ void __launch_bounds__(256) accumulate_h2_vec4_kernel(
   }
 }
 
-// Whole-batch variant of the fast path: one thread owns 4 consecutive z voxels of the ACCUMULATOR (inside the
-// bounding box of the batch's tiles) and applies every tile of the batch that covers them, in tile order — the
-// same per-voxel summation order as one launch per tile, but the accumulator is read and written once per batch
-// and there are no launch gaps.  Same preconditions as accumulate_h2_vec4_kernel for every tile.
-__global__ void __launch_bounds__(256) accumulate_batch_h2_vec4_kernel(
-    const __half* __restrict__ preds_all, TileRound tr, int bx0, int by0, int bz0, int bX, int bY, int bZ, int pX,
-    int pY, int pZ, FlipList flips, int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X,
-    int Y, int Z) {
-  const int zq = bZ >> 2;
-  const size_t nthreads = (size_t)bX * bY * zq;
-  const size_t pvox = (size_t)pX * pY * pZ;
-  const size_t hstride = (size_t)X * Y * Z;
-  const float nf = (float)n_flips;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int gz = bz0 + ((int)(i % zq) << 2);
-    const int gy = by0 + (int)((i / zq) % bY);
-    const int gx = bx0 + (int)(i / ((size_t)zq * bY));
-    float4 v0, v1;
-    bool touched = false;
-    const size_t a = ((size_t)gx * Y + gy) * Z + gz;
-    for (int t = 0; t < tr.n; ++t) {
-      const int x = gx - tr.sx[t], y = gy - tr.sy[t], z = gz - tr.sz[t];
-      if (x < 0 || x >= pX || y < 0 || y >= pY || z < 0 || z >= pZ) continue;
-      if (!touched) {
-        v0 = *reinterpret_cast<const float4*>(acc + a);
-        v1 = *reinterpret_cast<const float4*>(acc + hstride + a);
-        touched = true;
-      }
-      const __half* preds = preds_all + (size_t)tr.idx[t] * n_flips * pvox * 2;
-      float s0[4], s1[4];
-#pragma unroll
-      for (int f = 0; f < 8; ++f) {
-        if (f < n_flips) {
-          const int m = flips.m[f];
-          const int fx = (m & 1) ? pX - 1 - x : x;
-          const int fy = (m & 2) ? pY - 1 - y : y;
-          const bool rz = (m & 4) != 0;
-          const int fz = rz ? pZ - 4 - z : z;
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(preds + ((size_t)f * pvox + ((size_t)fx * pY + fy) * pZ + fz) * 2));
-          const __half2* hp = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 v = __half22float2(hp[rz ? 3 - k : k]);
-            if (f == 0) {
-              s0[k] = v.x;
-              s1[k] = v.y;
-            } else {
-              s0[k] = __fadd_rn(s0[k], v.x);
-              s1[k] = __fadd_rn(s1[k], v.y);
-            }
-          }
-        }
-      }
-      float g[4] = {1.f, 1.f, 1.f, 1.f};
-      if (gauss) {
-        const uint2 graw = __ldg(reinterpret_cast<const uint2*>(gauss + ((size_t)x * pY + y) * pZ + z));
-        const __half2* gp = reinterpret_cast<const __half2*>(&graw);
-        const float2 g01 = __half22float2(gp[0]), g23 = __half22float2(gp[1]);
-        g[0] = g01.x; g[1] = g01.y; g[2] = g23.x; g[3] = g23.y;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (n_flips > 1) {
-          s0[k] = __fdiv_rn(s0[k], nf);
-          s1[k] = __fdiv_rn(s1[k], nf);
-        }
-        if (gauss) {
-          s0[k] = __fmul_rn(s0[k], g[k]);
-          s1[k] = __fmul_rn(s1[k], g[k]);
-        }
-      }
-      v0.x = __fadd_rn(v0.x, s0[0]); v0.y = __fadd_rn(v0.y, s0[1]);
-      v0.z = __fadd_rn(v0.z, s0[2]); v0.w = __fadd_rn(v0.w, s0[3]);
-      v1.x = __fadd_rn(v1.x, s1[0]); v1.y = __fadd_rn(v1.y, s1[1]);
-      v1.z = __fadd_rn(v1.z, s1[2]); v1.w = __fadd_rn(v1.w, s1[3]);
-    }
-    if (touched) {
-      *reinterpret_cast<float4*>(acc + a) = v0;
-      *reinterpret_cast<float4*>(acc + hstride + a) = v1;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // weight sum (n_predictions): gather over the covering tiles, in tile order.
 // ------------------------------------------------------------------------------------------------
@@ -506,28 +422,6 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
     FNNU_CHECK_ARG(sx >= 0 && sy >= 0 && sz >= 0 && sx + pX <= X && sy + pY <= Y && sz + pZ <= Z,
                    "accumulate: tile %d (%d,%d,%d) outside the volume", t, sx, sy, sz);
     if (sz % 4 != 0) vec = false;
-  }
-  if (vec && n_tiles > 1 && n_tiles <= FNNU_ROUND_MAX) {
-    TileRound tr;
-    tr.n = n_tiles;
-    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {0, 0, 0};
-    for (int t = 0; t < n_tiles; ++t) {
-      tr.sx[t] = starts_host[t * 3]; tr.sy[t] = starts_host[t * 3 + 1]; tr.sz[t] = starts_host[t * 3 + 2];
-      tr.idx[t] = t;
-      for (int ax = 0; ax < 3; ++ax) {
-        int v = starts_host[t * 3 + ax];
-        if (v < lo[ax]) lo[ax] = v;
-        if (v + patch[ax] > hi[ax]) hi[ax] = v + patch[ax];
-      }
-    }
-    const size_t bbox = (size_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-    if (bbox <= 2 * (size_t)n_tiles * pvox) {     // a batch that wraps around a tile row has a sparse bounding box
-      accumulate_batch_h2_vec4_kernel<<<grid_for(bbox / 4, 256, 32), 256, 0, s>>>(
-          (const __half*)preds, tr, lo[0], lo[1], lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], pX, pY, pZ, fl,
-          n_flips, (const __half*)gaussian, (float*)acc, X, Y, Z);
-      FNNU_LAUNCH_CHECK();
-      return FNNU_OK;
-    }
   }
   // rounds: round[t] = 1 + max round of the earlier tiles that overlap t (0 if none)
   std::vector<int> round(n_tiles, 0);

@@ -319,12 +319,6 @@ class nnUNetPredictor(object):
     def _accumulate_rounds(starts, patch) -> int:
         """Number of kernels fnnu_accumulate_tiles launches for these tiles: tiles are applied in rounds of mutually
         non-overlapping tiles (round = 1 + max round of the earlier overlapping tiles), at most 8 tiles per launch."""
-        n = len(starts)
-        if 1 < n <= 8 and patch[2] % 4 == 0 and all(int(s[2]) % 4 == 0 for s in starts):
-            lo = [min(int(s[a]) for s in starts) for a in range(3)]
-            hi = [max(int(s[a]) + patch[a] for s in starts) for a in range(3)]
-            if (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) <= 2 * n * patch[0] * patch[1] * patch[2]:
-                return 1      # whole-batch kernel (2 heads fast path); an upper bound otherwise
         rounds = []
         for t, s in enumerate(starts):
             r = 0
