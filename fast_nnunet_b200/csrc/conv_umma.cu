@@ -17,9 +17,8 @@
 // MMAs; 4 epilogue warps drain TMEM (tcgen05.ld), add the bias, round to fp16, store channels-last and
 // accumulate the InstanceNorm sums of the rounded values (fp32 partials -> fp64 atomics).
 //
-// Warp roles (544 threads): warps 0-7 producers, warps 8-15 epilogue in two sets that split the M-tiles (TMEM lane
-// quarter = warp % 4; the per-tile drain chain is latency-bound, so two sets run it twice in parallel), warp 16 MMA
-// issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
+// Warp roles (416 threads): warps 0-7 producers, warps 8-11 epilogue (TMEM lane quarter = warp % 4),
+// warp 12 MMA issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
 // and MMA; TMEM accumulator buffers (full/empty mbarriers) between MMA and epilogue.
 //
 // Strided convolutions keep the same structure through a phase decomposition: with stride s the tap k
@@ -67,9 +66,8 @@ struct UmmaArgs {
 
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kEpiSets = 2;                        // epilogue warp sets: set s drains the M-tiles i = s (mod 2)
-constexpr int kEpilogueThreads = 128 * kEpiSets;
-constexpr int kMmaWarp = kProducerWarps + 4 * kEpiSets;
+constexpr int kEpilogueThreads = 128;
+constexpr int kMmaWarp = kProducerWarps + 4;
 constexpr int kThreadsUmma = (kMmaWarp + 1) * 32;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -410,8 +408,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   } else {
     // =========================== EPILOGUE ===========================
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - kProducerThreads;   // 0..255
-    const int eset = (warp - kProducerWarps) >> 2;
+    const int et = threadIdx.x - kProducerThreads;   // 0..127
     int buf = 0;
     uint32_t tphase0 = 0, tphase1 = 0;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
@@ -445,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
         const bool full16 = co0 + 16 <= a.cout;
         __half* out_plane = out_b + (size_t)oz * Hout * Wout * a.dst_cs;
-        for (int i = eset; i < c.T; i += kEpiSets) {
+        for (int i = 0; i < c.T; ++i) {
           const int pos = (int)tile_tab[i] + wq * 32 + lane;
           const int yo = (int)__umulhi((unsigned)pos, c.pitch_magic);
           const int xo = pos - yo * c.pitch;

@@ -10,12 +10,10 @@
 //   out[y][x, co] = D'[y - 1][x, (2, co)] + D'[y][x, (1, co)] + D'[y + 1][x, (0, co)]
 // is a sum of three accumulator tiles AT THE SAME LANE, done by the epilogue while it drains TMEM — no
 // cross-lane traffic.  Because an input row now feeds exactly one accumulator tile, the kernel streams:
-//   producers (8 warps in 4 or 2 groups): one smem stage = one input row x 3 z-planes x Cin, normalise-on-load
+//   producers (16 warps in 8 or 4 groups): one smem stage = one input row x 3 z-planes x Cin, normalise-on-load
 //   MMA warp: 9 * Cin/16 MMAs per stage into a ring of TMEM tile slots, commit per row
-//   epilogue (3 sets of 4 warps, rows round-robin): output row y as soon as tile y+1 is complete; frees tile y-1
+//   epilogue (4 warps): output row y as soon as tile y+1 is complete; frees tile y-1
 // Weights (all 27 taps) stay resident in shared memory for the whole kernel (<= 64 KB).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "ops.cuh"
 #include "umma_ptx.cuh"
@@ -35,7 +33,6 @@ struct RowsCfg {
   int slots;              // TMEM tile slots (Nf columns each)
   int n_yseg, seg_rows;
   int smem_bytes;
-  int dbg;                // FNNU_ROWS_DBG bit 0: skip the in-place normalise, bit 1: one MMA per row (timing experiments)
   int occ;                // CTAs per SM this launch is planned for (1 or 2): halves smem / TMEM budgets
   int tmem_cols;
 };
@@ -46,20 +43,14 @@ struct RowsArgs {
   int n_units;
 };
 
-// Warp roles.  Timing experiments (FNNU_ROWS_DBG) showed that with neither the normalise pass nor 8 of the 9 MMAs
-// the kernel is barely faster: the per-row EPILOGUE chain (barrier wait -> 3 TMEM loads -> convert -> store ->
-// release) is latency-bound when one set of 4 warps walks the rows one after the other.  So three sets of 4 epilogue
-// warps take the output rows round-robin.
-//   warps 0-7   producers, in groups of 64 * CHUNKS threads (4 groups for Cin 16, 2 for Cin 32)
-//   warps 8-19  epilogue: set s = (warp - 8) / 4 handles output rows yo = s (mod 3); TMEM lane quarter = warp % 4
-//   warp  20    MMA issuer (+ TMEM allocation); warps 21-23 only donate registers
-constexpr int kRowsProducerWarps = 8;
+// 16 producer warps (the producers are latency-bound: ncu shows them busy ~85 % at one instruction per ~8 cycles
+// per warp), dealt in groups of 64 * CHUNKS threads (8 groups for Cin 16, 4 groups for Cin 32) so that a thread
+// always covers a row in 5 steps of 32 positions.  Warps 16-19: epilogue, warp 20: MMA.
+constexpr int kRowsProducerWarps = 16;
 constexpr int kRowsProducerThreads = kRowsProducerWarps * 32;
-constexpr int kRowsEpiSets = 3;
-constexpr int kRowsMmaWarp = kRowsProducerWarps + 4 * kRowsEpiSets;
-constexpr int kRowsThreads = 24 * 32;
-// setmaxnreg budgets (launch: 768 x 80): 256 x 72 + 384 x 96 + 128 x 40 = 60416 <= 61440
-constexpr int kRegsProducer = 72, kRegsMma = 40, kRegsEpilogue = 96;
+constexpr int kRowsMmaWarp = kRowsProducerWarps + 4;
+constexpr int kRowsThreads = 24 * 32;   // 6 warpgroups: 4 producer, 1 epilogue, 1 holding the MMA warp (+3 idle warps)
+constexpr int kRegsProducer = 72, kRegsMma = 40, kRegsEpilogue = 152;   // setmaxnreg: 512 x 72 + 128 x 40 + 128 x 152 = 768 x 80
 __host__ __device__ constexpr int rows_group_threads(int chunks) { return 64 * chunks; }
 __host__ __device__ constexpr int rows_groups(int chunks) { return kRowsProducerThreads / (64 * chunks); }
 constexpr int kRowsMaxStages = 16;
@@ -110,7 +101,6 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   c.n_yseg = 1;
   while ((long long)a.batch * c.D * c.n_yseg < 3LL * num_sms() && c.H / (c.n_yseg * 2) >= 8) c.n_yseg *= 2;
   c.seg_rows = (c.H + c.n_yseg - 1) / c.n_yseg;
-  { const char* e = getenv("FNNU_ROWS_DBG"); c.dbg = e ? atoi(e) : 0; }
   c.ok = 1;
   return true;
 }
@@ -213,7 +203,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     auto finish_pending = [&](int keep_in_flight) {
       if (pend_stage < 0) return;
       if (keep_in_flight) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-      if (pend_row_ok && !(c.dbg & 1)) {
+      if (pend_row_ok) {
         uint8_t* st = ring + (size_t)pend_stage * c.stage_bytes + my_off;
 #pragma unroll
         for (int kz = 0; kz < 3; ++kz) {
@@ -328,7 +318,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
                 (void)dummy;
                 const uint32_t a_off = (uint32_t)((kz * (int)kQ + kc * 2) * (int)kProw + kx);
                 const uint32_t b_off = (uint32_t)((((kz * 3 + kx) * CHUNKS + kc) * 2) * (int)kNf);
-                if (!(c.dbg & 2) || accum == 0) umma_f16(d, da_st + a_off, b_desc0 + b_off, idesc, accum);
+                umma_f16(d, da_st + a_off, b_desc0 + b_off, idesc, accum);
                 accum = 1;
               }
             }
@@ -346,7 +336,6 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     // =========================== EPILOGUE ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int wq = warp & 3;
-    const int eset = (warp - kRowsProducerWarps) >> 2;   // which third of the rows this warp handles
     const int x = wq * 32 + lane;                   // output column == TMEM lane
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
@@ -385,8 +374,8 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         cur_b = b;
       }
       const int n_out = yb - ya;
-      __half* out_px = a.dst + (((size_t)b * c.D + z) * c.H + ya + eset) * out_row_stride + (size_t)x * a.dst_cs;
-      for (int yo = eset; yo < n_out; yo += kRowsEpiSets, out_px += kRowsEpiSets * out_row_stride) {
+      __half* out_px = a.dst + (((size_t)b * c.D + z) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs;
+      for (int yo = 0; yo < n_out; ++yo, out_px += out_row_stride) {
         // unit tiles yo, yo+1, yo+2 hold input rows y-1, y, y+1; MMAs complete in order: wait for the last
         const long long t2 = tile_counter + yo + 2;
         mbar_wait(&tfull_bar[(int)(t2 % c.slots)], (uint32_t)((t2 / c.slots) & 1));
@@ -438,10 +427,10 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         tc_fence_before();
         mbar_arrive(&tempty_bar[(int)((tile_counter + yo) % c.slots)]);
       }
-      // the last two tiles of the unit have no later consumer: the sets whose turn it would be release them
+      // the last two tiles of the unit have no later consumer
       tc_fence_before();
-      if (n_out % kRowsEpiSets == eset) mbar_arrive(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
-      if ((n_out + 1) % kRowsEpiSets == eset) mbar_arrive(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
+      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
+      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
       tile_counter += n_out + 2;
     }
     flush_stats(cur_b);
