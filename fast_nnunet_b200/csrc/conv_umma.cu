@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&full_bar[s], kProducerWarps);       // one arrival per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpilogueThreads);
+      mbar_init(&tempty_bar[i], kEpilogueThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&full_bar[stage]);
+          mbar_arrive_warp(&full_bar[stage]);
           if (++stage == c.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(buf ? &tempty_bar[1] : &tempty_bar[0]);
+      mbar_arrive_warp(buf ? &tempty_bar[1] : &tempty_bar[0]);
       if (c.tmem_bufs == 2) buf ^= 1;
       if (a.dst_stats) {
         named_bar_sync(2, kEpilogueThreads);

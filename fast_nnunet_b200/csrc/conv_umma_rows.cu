@@ -127,12 +127,12 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
-      mbar_init(&full_bar[s], rows_group_threads(CHUNKS));
+      mbar_init(&full_bar[s], rows_group_threads(CHUNKS) / 32);   // one arrival per producer warp of the group
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < c.slots; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 4);                                // one arrival per epilogue warp
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&full_bar[pend_stage]);
+      mbar_arrive_warp(&full_bar[pend_stage]);
       pend_stage = -1;
     };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -425,12 +425,12 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         }
         // unit tile yo is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
         tc_fence_before();
-        mbar_arrive(&tempty_bar[(int)((tile_counter + yo) % c.slots)]);
+        mbar_arrive_warp(&tempty_bar[(int)((tile_counter + yo) % c.slots)]);
       }
       // the last two tiles of the unit have no later consumer
       tc_fence_before();
-      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
-      mbar_arrive(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
+      mbar_arrive_warp(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
+      mbar_arrive_warp(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
       tile_counter += n_out + 2;
     }
     flush_stats(cur_b);
