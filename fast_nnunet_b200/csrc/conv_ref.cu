@@ -258,11 +258,12 @@ __global__ void __launch_bounds__(128) conv_small_cin_kernel(ConvArgs a) {
   const long long n_groups = (long long)D0 * D1 * gpr;
   const long long gidx = (long long)blockIdx.x * 128 + threadIdx.x;
   const bool active = gidx < n_groups;
-  float acc[4][16];
+  // accumulators as (o, o+1) pairs: Blackwell's packed fp32 FMA (fma.rn.f32x2) does two FMAs per instruction
+  unsigned long long acc2[4][8];
 #pragma unroll
   for (int v = 0; v < 4; ++v)
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[v][o] = 0.f;
+    for (int o = 0; o < 8; ++o) acc2[v][o] = 0ull;
   int x0 = 0, y = 0, z = 0;
   if (active) {
     x0 = (int)(gidx % gpr) * 4;
@@ -292,13 +293,18 @@ __global__ void __launch_bounds__(128) conv_small_cin_kernel(ConvArgs a) {
           const int tap = (kz * a.k[1] + ky) * a.k[2] + kx;
 #pragma unroll
           for (int c = 0; c < CIN; ++c) {
-            const float4* wt = reinterpret_cast<const float4*>(w_s + ((size_t)tap * CIN + c) * 16);
-            float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
-            float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+            const ulonglong2* wt = reinterpret_cast<const ulonglong2*>(w_s + ((size_t)tap * CIN + c) * 16);
+            const ulonglong2 w01 = wt[0], w23 = wt[1], w45 = wt[2], w67 = wt[3];
+            const unsigned long long wp[8] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y};
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
+            for (int v = 0; v < 4; ++v) {
+              const unsigned int ib = __float_as_uint(in[v + kx][c]);
+              unsigned long long a2;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "r"(ib));
 #pragma unroll
-              for (int o = 0; o < 16; ++o) acc[v][o] = fmaf(in[v + kx][c], wv[o], acc[v][o]);
+              for (int o = 0; o < 8; ++o)
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[v][o]) : "l"(a2), "l"(wp[o]));
+            }
           }
         }
       }
@@ -317,7 +323,8 @@ __global__ void __launch_bounds__(128) conv_small_cin_kernel(ConvArgs a) {
       __half hv[16];
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
-        float val = acc[v][o] + ((a.bias && co0 + o < a.cout) ? __ldg(a.bias + co0 + o) : 0.f);
+        const float accv = __uint_as_float((o & 1) ? (unsigned int)(acc2[v][o >> 1] >> 32) : (unsigned int)(acc2[v][o >> 1]));
+        float val = accv + ((a.bias && co0 + o < a.cout) ? __ldg(a.bias + co0 + o) : 0.f);
         hv[o] = __float2half_rn(val);
         float r = __half2float(hv[o]);
         s1[o] += r;
