@@ -33,14 +33,22 @@ TEACHER_FEATS = [32, 64, 128, 256, 320, 320]
 ISO_K = [[3, 3, 3]] * 6
 ISO_S = [[1, 1, 1]] + [[2, 2, 2]] * 5
 
+BONE_K = [[1, 3, 3]] + [[3, 3, 3]] * 5
+BONE_S = [[1, 1, 1], [1, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2], [2, 1, 1]]
+
 WORKLOADS = {
-    # name: (volume (C,X,Y,Z), features, kernels, strides, patch, heads, description)
+    # name: (volume (C,X,Y,Z), features, kernels, strides, patch, heads, description[, ResEnc blocks per stage])
     'cfg1': ((1, 160, 160, 160), STUDENT_FEATS, ISO_K, ISO_S, (128, 128, 128), 2,
              'student r=2 PlainConvUNet, 1x160^3 CT, 128^3 patches, step 0.5, mirror TTA'),
     'cfg2': ((1, 400, 512, 512), STUDENT_FEATS, ISO_K, ISO_S, (128, 128, 128), 2,
              'student r=2 PlainConvUNet, 512x512x400 CT, 128^3 patches, step 0.5, mirror TTA'),
     'cfg3': ((1, 400, 512, 512), TEACHER_FEATS, ISO_K, ISO_S, (128, 128, 128), 2,
              'teacher PlainConvUNet, 512x512x400 CT, 128^3 patches, step 0.5, mirror TTA'),
+    'cfg4': ((4, 155, 240, 240), STUDENT_FEATS, ISO_K, ISO_S, (128, 128, 128), 4,
+             'ResEnc-M student r=2 (blocks 1,3,4,6,6,6), 4-channel MRI 240x240x155, 128^3 patches, mirror TTA',
+             [1, 3, 4, 6, 6, 6]),
+    'cfg5': ((1, 1200, 512, 512), STUDENT_FEATS, BONE_K, BONE_S, (160, 96, 96), 61,
+             'bone_turbo-shaped r=2 PlainConvUNet, 61 labels, 512x512x1200 CT, 160x96x96 patches, mirror TTA'),
 }
 
 
@@ -113,11 +121,13 @@ def measured_peaks():
 
 def build_folder(tmp, wl):
     from fast_nnunet_b200 import model_folder as M
-    vol, feats, ks, ss, patch, heads, _ = WORKLOADS[wl]
-    kw = M.plain_arch_kwargs(feats, ks, ss)
-    sd = M.synthesize_state_dict(M.PLAIN, kw, vol[0], heads, seed=1234)
+    vol, feats, ks, ss, patch, heads = WORKLOADS[wl][:6]
+    blocks = WORKLOADS[wl][7] if len(WORKLOADS[wl]) > 7 else None
+    cls = M.RESENC if blocks else M.PLAIN
+    kw = M.resenc_arch_kwargs(feats, ks, ss, blocks) if blocks else M.plain_arch_kwargs(feats, ks, ss)
+    sd = M.synthesize_state_dict(cls, kw, vol[0], heads, seed=1234)
     folder = os.path.join(tmp, 'nnUNetTrainer__nnUNetPlans__3d_fullres')
-    M.write_model_folder(folder, M.PLAIN, kw, patch, sd, vol[0], heads)
+    M.write_model_folder(folder, cls, kw, patch, sd, vol[0], heads)
     return folder, kw, sd
 
 
@@ -131,10 +141,12 @@ def cpu_reference_sample(wl, n_tiles_sample, threads, seed_vol=0):
     from fast_nnunet_b200 import sliding_window as sw
     from oracle import networks as N
     from oracle import predictor as OP
-    vol, feats, ks, ss, patch, heads, _ = WORKLOADS[wl]
-    kw = M.plain_arch_kwargs(feats, ks, ss)
-    sd = M.synthesize_state_dict(M.PLAIN, kw, vol[0], heads, seed=1234)
-    net = N.build_from_arch(M.PLAIN, kw, vol[0], heads, allow_init=False)
+    vol, feats, ks, ss, patch, heads = WORKLOADS[wl][:6]
+    blocks = WORKLOADS[wl][7] if len(WORKLOADS[wl]) > 7 else None
+    cls = M.RESENC if blocks else M.PLAIN
+    kw = M.resenc_arch_kwargs(feats, ks, ss, blocks) if blocks else M.plain_arch_kwargs(feats, ks, ss)
+    sd = M.synthesize_state_dict(cls, kw, vol[0], heads, seed=1234)
+    net = N.build_from_arch(cls, kw, vol[0], heads, allow_init=False)
     net.load_state_dict(sd)
     net.eval()
     n_total = len(sw.tile_starts(vol[1:], patch, 0.5))
@@ -189,7 +201,7 @@ def run_ours(args, wl):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    vol, feats, ks, ss, patch, heads, desc = WORKLOADS[wl]
+    vol, feats, ks, ss, patch, heads, desc = WORKLOADS[wl][:7]
     nvox = float(np.prod(vol[1:]))
 
     with tempfile.TemporaryDirectory() as tmp:
@@ -318,7 +330,8 @@ def run_ours(args, wl):
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'fp16 storage / fp32 accumulate (tcgen05 kind::f16)', 'data': 'synthetic',
             'config': {'workload': desc, 'tiles': n_tiles, 'mirror_passes': 8, 'tiles_per_batch': pred.last_tiles_per_batch,
-                       'l2': 'inputs larger than L2 (volume 419 MB, activations 3.7 GB per batch)',
+                       'l2': f'inputs larger than L2 (volume {host.numel() * 4 / 1e6:.0f} MB, activations '
+                             f'{prog.activation_elements() * 2 * pred.last_tiles_per_batch * 8 / 1e9:.1f} GB per launch sequence)',
                        'parallelism': f'x-slab tile sharding over {world} GPU(s), one halo exchange'},
             'e2e': {'value': nvox / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mvoxel/s', 'sec_per_volume': e2e_ms * 1e-3,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
