@@ -510,7 +510,7 @@ int launch_pack_weights_direct(const float* w_dev, float* out, int cin, int cout
 // residual join: dst = lrelu_slope(xform(a) + xform(b)), stored ready to use
 // average pooling: dst = mean over the stride window of xform(src), stored ready to use
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) add_act_kernel(EltArgs a) {
+__global__ void __launch_bounds__(256) add_act_scalar_kernel(EltArgs a) {
   const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
   const size_t total = nv * a.c * a.batch;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) add_act_kernel(EltArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) avgpool_kernel(EltArgs a) {
+__global__ void __launch_bounds__(256) avgpool_scalar_kernel(EltArgs a) {
   // a.d = OUTPUT dims; input dims = a.d * a.s
   const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
   const size_t total = nv * a.c * a.batch;
@@ -556,11 +556,122 @@ __global__ void __launch_bounds__(256) avgpool_kernel(EltArgs a) {
   }
 }
 
+// Both kernels: blockIdx.y = sample; the per-channel transforms are evaluated ONCE per block into shared memory
+// (they involve fp64 mean / rsqrt), then each thread streams 8 channels of a voxel with 128-bit accesses.
+__device__ __forceinline__ void elt_tables(const EltArgs& a, int b, float* t, bool second) {
+  // t: [scale | shift | slope][c]
+  const double* st = second ? a.src2_stats : a.src_stats;
+  const ChanMeta* mt = second ? a.src2_meta : a.src_meta;
+  const int stride = second ? a.src2_stat_stride : a.src_stat_stride;
+  for (int c = threadIdx.x; c < a.c; c += blockDim.x) {
+    float sc, sh;
+    const ChanMeta m = mt[c];
+    xform_from_stats(st + ((size_t)b * stride + c) * 2, m, a.inv_count, sc, sh);
+    t[c] = sc;
+    t[a.c + c] = sh;
+    t[2 * a.c + c] = m.eps < 0.f ? 1.f : m.slope;
+  }
+}
+
+__global__ void __launch_bounds__(256) add_act_kernel(EltArgs a) {
+  extern __shared__ float tab[];            // [2 sources][3][c]
+  const int b = blockIdx.y;
+  float* t1 = tab;
+  float* t2 = tab + 3 * a.c;
+  elt_tables(a, b, t1, false);
+  elt_tables(a, b, t2, true);
+  __syncthreads();
+  const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
+  const int groups = a.c >> 3;
+  const size_t total = nv * groups;
+  const __half* s1 = a.src + (size_t)b * nv * a.src_cs;
+  const __half* s2 = a.src2 + (size_t)b * nv * a.src2_cs;
+  __half* d = a.dst + (size_t)b * nv * a.dst_cs;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const size_t v = i / groups;
+    const int c0 = g * 8;
+    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(s1 + v * a.src_cs + c0));
+    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(s2 + v * a.src2_cs + c0));
+    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&r2);
+    __half2 o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f1 = __half22float2(h1[e]), f2 = __half22float2(h2[e]);
+      const int c = c0 + 2 * e;
+      const float x0 = lrelu(fmaf(f1.x, t1[c], t1[a.c + c]), t1[2 * a.c + c]) + lrelu(fmaf(f2.x, t2[c], t2[a.c + c]), t2[2 * a.c + c]);
+      const float x1 = lrelu(fmaf(f1.y, t1[c + 1], t1[a.c + c + 1]), t1[2 * a.c + c + 1]) +
+                       lrelu(fmaf(f2.y, t2[c + 1], t2[a.c + c + 1]), t2[2 * a.c + c + 1]);
+      o[e] = __floats2half2_rn(lrelu(x0, a.slope), lrelu(x1, a.slope));
+    }
+    *reinterpret_cast<uint4*>(d + v * a.dst_cs + c0) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_kernel(EltArgs a) {
+  // a.d = OUTPUT dims; input dims = a.d * a.s
+  extern __shared__ float tab[];
+  const int b = blockIdx.y;
+  elt_tables(a, b, tab, false);
+  __syncthreads();
+  const size_t nv = (size_t)a.d[0] * a.d[1] * a.d[2];
+  const int I1 = a.d[1] * a.s[1], I2 = a.d[2] * a.s[2];
+  const size_t nvi = nv * a.s[0] * a.s[1] * a.s[2];
+  const float inv = 1.f / (float)(a.s[0] * a.s[1] * a.s[2]);
+  const int groups = a.c >> 3;
+  const size_t total = nv * groups;
+  const __half* src = a.src + (size_t)b * nvi * a.src_cs;
+  __half* d = a.dst + (size_t)b * nv * a.dst_cs;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const size_t v = i / groups;
+    const int c0 = g * 8;
+    const int x = (int)(v % a.d[2]);
+    const int y = (int)((v / a.d[2]) % a.d[1]);
+    const int z = (int)(v / ((size_t)a.d[2] * a.d[1]));
+    float sum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum[e] = 0.f;
+    for (int dz = 0; dz < a.s[0]; ++dz)
+      for (int dy = 0; dy < a.s[1]; ++dy)
+        for (int dx = 0; dx < a.s[2]; ++dx) {
+          const size_t iv = ((size_t)(z * a.s[0] + dz) * I1 + (y * a.s[1] + dy)) * I2 + (x * a.s[2] + dx);
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(src + iv * a.src_cs + c0));
+          const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            const int c = c0 + 2 * e;
+            sum[2 * e] += lrelu(fmaf(f.x, tab[c], tab[a.c + c]), tab[2 * a.c + c]);
+            sum[2 * e + 1] += lrelu(fmaf(f.y, tab[c + 1], tab[a.c + c + 1]), tab[2 * a.c + c + 1]);
+          }
+        }
+    __half2 o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(sum[2 * e] * inv, sum[2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(d + v * a.dst_cs + c0) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+static bool elt_vec_ok(const EltArgs& a) {
+  return a.c % 8 == 0 && a.src_cs % 8 == 0 && a.dst_cs % 8 == 0 && ((uintptr_t)a.src % 16) == 0 && ((uintptr_t)a.dst % 16) == 0 &&
+         (!a.src2 || (a.src2_cs % 8 == 0 && ((uintptr_t)a.src2 % 16) == 0)) && a.c <= 2048;
+}
+
 int launch_add_act(const EltArgs& a, cudaStream_t s) {
   size_t total = (size_t)a.d[0] * a.d[1] * a.d[2] * a.c * a.batch;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  add_act_kernel<<<blocks, 256, 0, s>>>(a);
+  if (elt_vec_ok(a)) {
+    size_t work = (size_t)a.d[0] * a.d[1] * a.d[2] * (a.c / 8);
+    int bx = (int)((work + 255) / 256);
+    if (bx > num_sms() * 8) bx = num_sms() * 8;
+    add_act_kernel<<<dim3((unsigned)bx, (unsigned)a.batch), 256, (size_t)6 * a.c * sizeof(float), s>>>(a);
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
+  add_act_scalar_kernel<<<blocks, 256, 0, s>>>(a);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }
@@ -569,7 +680,15 @@ int launch_avgpool(const EltArgs& a, cudaStream_t s) {
   size_t total = (size_t)a.d[0] * a.d[1] * a.d[2] * a.c * a.batch;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  avgpool_kernel<<<blocks, 256, 0, s>>>(a);
+  if (elt_vec_ok(a)) {
+    size_t work = (size_t)a.d[0] * a.d[1] * a.d[2] * (a.c / 8);
+    int bx = (int)((work + 255) / 256);
+    if (bx > num_sms() * 8) bx = num_sms() * 8;
+    avgpool_kernel<<<dim3((unsigned)bx, (unsigned)a.batch), 256, (size_t)3 * a.c * sizeof(float), s>>>(a);
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
+  avgpool_scalar_kernel<<<blocks, 256, 0, s>>>(a);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }
