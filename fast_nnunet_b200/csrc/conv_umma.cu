@@ -340,9 +340,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    // The whole warp runs the (uniform) control flow; lane 0 issues.  Per MMA: one 64-bit add on the A
-    // descriptor and one add on the TMEM column, both warp-uniform.
-    const bool leader = lane == 0;
+    // The whole warp runs the (uniform) control flow; one lane, chosen with elect.sync, issues (ptxas then knows a
+    // single thread executes the UTCHMMAs and does not wrap each one in an R2UR serialisation loop).  Per MMA: one
+    // 64-bit add on the A descriptor and one add on the TMEM column, both warp-uniform.
     const uint32_t idesc = (1u << 4) | ((uint32_t)(c.Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a_lbo = (uint32_t)c.P_alloc * 16, b_lbo = (uint32_t)c.Nc * 16;
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + (size_t)stage * stage_bytes);
           const uint32_t b_base = a_base + (uint32_t)c.a_stage_bytes;
-          if (leader) {
+          if (elect_one()) {
           for (int kc = 0; kc < c.KC; ++kc) {
             for (int t = 0; t < c.ntyx; ++t) {
               const uint64_t db = b_desc0 + (uint64_t)((b_base + (uint32_t)((kc * c.ntyx + t) * 2) * b_lbo) >> 4);
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           if (++stage == c.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (leader) umma_commit(buf ? &tfull_bar[1] : &tfull_bar[0]);
+      if (elect_one()) umma_commit(buf ? &tfull_bar[1] : &tfull_bar[0]);
       __syncwarp();
       if (buf) tphase1 ^= 1; else tphase0 ^= 1;
       if (c.tmem_bufs == 2) buf ^= 1;

@@ -49,6 +49,7 @@ struct RowsArgs {
 constexpr int kRowsProducerWarps = 16;
 constexpr int kRowsProducerThreads = kRowsProducerWarps * 32;
 constexpr int kRowsMmaWarp = kRowsProducerWarps + 4;
+constexpr int kRowsMmaIssuers = 1;      // issuing warps (rows dealt round-robin); 2 measured no faster: the tensor pipe, not the issue path, paces the MMAs
 constexpr int kRowsThreads = 24 * 32;   // 6 warpgroups: 4 producer, 1 epilogue, 1 holding the MMA warp (+3 idle warps)
 constexpr int kRegsProducer = 72, kRegsMma = 40, kRegsEpilogue = 152;   // setmaxnreg: 512 x 72 + 128 x 40 + 128 x 152 = 768 x 80
 __host__ __device__ constexpr int rows_group_threads(int chunks) { return 64 * chunks; }
@@ -193,7 +194,10 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     const uint32_t plane_bytes = (uint32_t)(c.Q * c.P_row) * 16u;
     const uint32_t my_off = (uint32_t)(q * c.P_row + xp0) * 16u;   // this thread's first item inside a plane
     const size_t row_bytes = (size_t)c.W * a.src_cs * 2;
-    long long row_counter = 0;                        // global stage sequence number
+    // ring position of the CTA's next row: group index, stage and phase are advanced incrementally (a 64-bit
+    // div/mod by a run-time value is a ~300-cycle subroutine; five of them per row bounded the kernel once)
+    int row_grp = 0, row_stage = 0;
+    uint32_t row_phase = 0;
     int cur_b = -1;
     __half2 s2[4], t2[4], l2[4];
     // Software pipeline, two stages deep per group: the raw row is fetched with cp.async (zero-filled outside the
@@ -247,10 +251,13 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         if (z + kz - c.pz >= 0 && z + kz - c.pz < c.D) zmask |= 1 << kz;
       const int n_rows = (yb - ya) + 2;
       const char* plane0 = reinterpret_cast<const char*>(a.src) + (((size_t)b * c.D + (z - c.pz)) * c.H) * row_bytes;
-      for (int j = 0; j < n_rows; ++j, ++row_counter) {
-        if ((int)(row_counter & (kGroups - 1)) != grp) continue;
-        const int stage = (int)(row_counter % c.stages);
-        const uint32_t phase = (uint32_t)((row_counter / c.stages) & 1);
+      for (int j = 0; j < n_rows; ++j) {
+        const int stage = row_stage;
+        const uint32_t phase = row_phase;
+        const bool mine = row_grp == grp;
+        row_grp = (row_grp + 1) & (kGroups - 1);
+        if (++row_stage == c.stages) { row_stage = 0; row_phase ^= 1; }
+        if (!mine) continue;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const int y_in = ya - 1 + j;
         const bool row_ok = y_in >= 0 && y_in < c.H;
@@ -278,7 +285,9 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
   } else if (warp >= kRowsMmaWarp) {
     // =========================== MMA ISSUER (warp 20; warps 21-23 only donate registers) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
-    if (warp == kRowsMmaWarp) {
+    if (warp < kRowsMmaWarp + kRowsMmaIssuers) {
+    // Rows are dealt round-robin to kRowsMmaIssuers issuing warps (each row has its own TMEM tile, so the rows are
+    // independent): one warp's issue path (R2UR + ELECT + UTCHMMA, ~65 cycles per MMA) is slower than the tensor pipe.
     // One elected lane issues; every descriptor offset of a row's 9 * CHUNKS MMAs is a compile-time constant
     // added to the stage base, so the issue path is ~a dozen instructions per MMA (the MMA itself occupies the
     // tensor pipe for ~64 cycles of operand fetch).
@@ -290,7 +299,8 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     const uint64_t b_desc0 = make_desc(smem_u32(w_s), kNf * 16, 128);
     const uint32_t stage_u16 = (uint32_t)c.stage_bytes >> 4;
     mbar_wait(w_bar, 0);
-    int stage = 0, slot = 0;
+    int stage = 0, slot = 0, turn = 0;
+    const int my_turn = warp - kRowsMmaWarp;
     uint32_t phase = 0, sphase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z, ya, yb;
@@ -300,12 +310,22 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
 #pragma unroll
       for (int kz = 0; kz < 3; ++kz) kzv[kz] = kz < c.nkz && (z + kz - c.pz) >= 0 && (z + kz - c.pz) < c.D;
       for (int j = 0; j < n_rows; ++j) {
+        const bool mine = turn == my_turn;
+        if (++turn == kRowsMmaIssuers) turn = 0;
+        if (!mine) {
+          if (++stage == c.stages) { stage = 0; phase ^= 1; }
+          if (++slot == c.slots) { slot = 0; sphase ^= 1; }
+          continue;
+        }
         mbar_wait(&tempty_bar[slot], sphase ^ 1);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem_base + (uint32_t)slot * kNf;
-          const uint64_t da_st = a_desc0 + (uint64_t)((uint32_t)stage * stage_u16);
+        // the two per-row values go through a lane-0 broadcast: ptxas then knows they are warp-uniform and feeds the
+        // UTCHMMA uniform-register operands directly instead of through a per-instruction R2UR "waterfall" loop
+        const uint32_t d = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)slot * kNf, 0);
+        const uint32_t da_lo = __shfl_sync(0xffffffffu, (uint32_t)a_desc0 + (uint32_t)stage * stage_u16, 0);
+        if (elect_one()) {
+          const uint64_t da_st = (a_desc0 & 0xffffffff00000000ull) | da_lo;
           uint32_t accum = 0;
 #pragma unroll
           for (int kz = 0; kz < 3; ++kz) {
@@ -339,7 +359,8 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     const int x = wq * 32 + lane;                   // output column == TMEM lane
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
-    long long tile_counter = 0;
+    int slot_a = 0;                                 // TMEM slot (and its phase) of the unit tile that holds row y-1
+    uint32_t phase_a = 0;
     int cur_b = -1;
     constexpr int kBiasRegs = CP == 16 ? 16 : 1;      // CP == 32: registers are needed for the partial sums
     float s1[CP], s2[CP], bias[kBiasRegs];
@@ -374,15 +395,30 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         cur_b = b;
       }
       const int n_out = yb - ya;
+      {
+        // tiles complete in issue order per issuing warp only: wait for every tile once (rows y-1 and y here, row
+        // y+1 inside the loop)
+        int sl = slot_a;
+        uint32_t ph = phase_a;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          mbar_wait(&tfull_bar[sl], ph);
+          if (++sl == c.slots) { sl = 0; ph ^= 1; }
+        }
+      }
       __half* out_px = a.dst + (((size_t)b * c.D + z) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs;
       for (int yo = 0; yo < n_out; ++yo, out_px += out_row_stride) {
         // unit tiles yo, yo+1, yo+2 hold input rows y-1, y, y+1; MMAs complete in order: wait for the last
-        const long long t2 = tile_counter + yo + 2;
-        mbar_wait(&tfull_bar[(int)(t2 % c.slots)], (uint32_t)((t2 / c.slots) & 1));
+        int slot_b = slot_a + 1;
+        uint32_t phase_c = phase_a;
+        if (slot_b == c.slots) { slot_b = 0; phase_c ^= 1; }
+        int slot_c = slot_b + 1;
+        if (slot_c == c.slots) { slot_c = 0; phase_c ^= 1; }
+        mbar_wait(&tfull_bar[slot_c], phase_c);
         tc_fence_after();
-        const uint32_t t_a = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo) % c.slots) * c.Nf);
-        const uint32_t t_b = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 1) % c.slots) * c.Nf);
-        const uint32_t t_c = tmem_base + lane_off + (uint32_t)((int)((tile_counter + yo + 2) % c.slots) * c.Nf);
+        const uint32_t t_a = tmem_base + lane_off + (uint32_t)(slot_a * (int)(3 * CP));
+        const uint32_t t_b = tmem_base + lane_off + (uint32_t)(slot_b * (int)(3 * CP));
+        const uint32_t t_c = tmem_base + lane_off + (uint32_t)(slot_c * (int)(3 * CP));
 #pragma unroll
         for (int g0 = 0; g0 < CP; g0 += 16) {
           // out(y) = D'[y-1][ky = 0] + D'[y][ky = 1] + D'[y+1][ky = 2]   (input row r feeds output row r - ky + 1)
@@ -425,13 +461,16 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         }
         // unit tile yo is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
         tc_fence_before();
-        mbar_arrive_warp(&tempty_bar[(int)((tile_counter + yo) % c.slots)]);
+        mbar_arrive_warp(&tempty_bar[slot_a]);
+        if (++slot_a == c.slots) { slot_a = 0; phase_a ^= 1; }
       }
       // the last two tiles of the unit have no later consumer
       tc_fence_before();
-      mbar_arrive_warp(&tempty_bar[(int)((tile_counter + n_out) % c.slots)]);
-      mbar_arrive_warp(&tempty_bar[(int)((tile_counter + n_out + 1) % c.slots)]);
-      tile_counter += n_out + 2;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        mbar_arrive_warp(&tempty_bar[slot_a]);
+        if (++slot_a == c.slots) { slot_a = 0; phase_a ^= 1; }
+      }
     }
     flush_stats(cur_b);
   }

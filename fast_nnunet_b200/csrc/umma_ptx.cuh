@@ -22,6 +22,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// elect.sync: true in exactly one lane of a converged warp.  Guarding tcgen05.mma / tcgen05.commit with THIS predicate
+// (rather than lane == 0) lets ptxas see that a single thread executes them; otherwise every UTCHMMA / UTCBAR is
+// wrapped in an ELECT + R2UR + BRA.U.ANY serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
