@@ -64,11 +64,15 @@ struct UmmaArgs {
   int n_units;
 };
 
-constexpr int kProducerWarps = 8;
+// Six warpgroups: 4 of producers (ncu: the producers are instruction-latency bound -- ~40 instructions per 16-byte
+// item at ~4.5 cycles each with 2 warps per scheduler -- so 16 warps instead of 8), 1 epilogue, 1 holding the MMA warp
+// (its 3 other warps only donate registers).  setmaxnreg: 512 x 80 + 128 x 120 + 128 x 40 <= 64 K registers.
+constexpr int kProducerWarps = 16;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kMmaWarp = kProducerWarps + 4;
-constexpr int kThreadsUmma = (kMmaWarp + 1) * 32;
+constexpr int kThreadsUmma = (kMmaWarp + 4) * 32;
+constexpr int kRegsProducerU = 80, kRegsMmaU = 40, kRegsEpilogueU = 120;
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline int tile_base_of(const UmmaCfg& c, int i) {
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 
   if (warp < kProducerWarps) {
     // =========================== PRODUCERS ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducerU));
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
     const int qshift = (Q == 2) ? 1 : (Q == 4 ? 2 : 3);
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           for (int phy = 0; phy < c.nph_y; ++phy) {
             for (int phx = 0; phx < c.nph_x; ++phx) {
               uint8_t* a_q = a_s + ((size_t)q * c.P_alloc + (size_t)(phy * c.nph_x + phx) * c.P_plane) * 16;
-              constexpr int U = 8;
+              constexpr int U = 4;
               for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
                 uint4 raw[U];
                 int pos[U];
@@ -338,8 +343,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp) {
     // =========================== MMA ISSUER ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMmaU));
+    if (warp == kMmaWarp) {
     // The whole warp runs the (uniform) control flow; one lane, chosen with elect.sync, issues (ptxas then knows a
     // single thread executes the UTCHMMAs and does not wrap each one in an R2UR serialisation loop).  Per MMA: one
     // 64-bit add on the A descriptor and one add on the TMEM column, both warp-uniform.
@@ -405,8 +412,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
       if (buf) tphase1 ^= 1; else tphase0 ^= 1;
       if (c.tmem_bufs == 2) buf ^= 1;
     }
+    }
   } else {
     // =========================== EPILOGUE ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogueU));
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
     const int et = threadIdx.x - kProducerThreads;   // 0..127
     int buf = 0;
