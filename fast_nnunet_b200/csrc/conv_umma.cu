@@ -30,6 +30,8 @@
 // Replaces the cuDNN calls behind `self.network(x)` (predict_from_raw_data.py:543) for Conv3d
 // (kernel 1|3, stride 1|2 per axis) and ConvTranspose3d (kernel == stride) layers with Cin % 16 == 0;
 // other shapes (the 1- or 4-channel first layer) run on conv_ref.cu.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "ops.cuh"
 #include "umma_ptx.cuh"
@@ -66,13 +68,14 @@ struct UmmaArgs {
 
 // Six warpgroups: 4 of producers (ncu: the producers are instruction-latency bound -- ~40 instructions per 16-byte
 // item at ~4.5 cycles each with 2 warps per scheduler -- so 16 warps instead of 8), 1 epilogue, 1 holding the MMA warp
-// (its 3 other warps only donate registers).  setmaxnreg: 512 x 80 + 128 x 120 + 128 x 40 <= 64 K registers.
+// (its 3 other warps only donate registers).  setmaxnreg: 512 x 88 + 128 x 88 + 128 x 40 = 768 x 80 registers (the producers
+// keep U = 8 16-byte loads in flight per thread: the stride-2 layer was bound by memory-level parallelism).
 constexpr int kProducerWarps = 16;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kMmaWarp = kProducerWarps + 4;
 constexpr int kThreadsUmma = (kMmaWarp + 4) * 32;
-constexpr int kRegsProducerU = 80, kRegsMmaU = 40, kRegsEpilogueU = 120;
+constexpr int kRegsProducerU = 88, kRegsMmaU = 40, kRegsEpilogueU = 88;   // must sum to <= 768 x 80: setmaxnreg moves registers inside the CTA's own allocation
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline int tile_base_of(const UmmaCfg& c, int i) {
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 
   if (warp < kProducerWarps) {
     // =========================== PRODUCERS ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducerU));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducerU));
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
     const int qshift = (Q == 2) ? 1 : (Q == 4 ? 2 : 3);
@@ -304,36 +307,41 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
             t2[e] = __floats2half2_rn(xh[ch0 + 2 * e], xh[ch0 + 2 * e + 1]);
             l2[e] = __floats2half2_rn(xl[ch0 + 2 * e], xl[ch0 + 2 * e + 1]);
           }
-          for (int phy = 0; phy < c.nph_y; ++phy) {
-            for (int phx = 0; phx < c.nph_x; ++phx) {
-              uint8_t* a_q = a_s + ((size_t)q * c.P_alloc + (size_t)(phy * c.nph_x + phx) * c.P_plane) * 16;
-              constexpr int U = 4;
-              for (int j0 = tid; j0 < items; j0 += kProducerThreads * U) {
-                uint4 raw[U];
-                int pos[U];
-                bool ok[U];
+          // all phase planes of the stage form ONE item space (a strided layer's planes are small: enc1.0 has 4 planes
+          // of 780 items for 512 threads, and looping over them one by one exposed a global-load latency per plane)
+          {
+            uint8_t* a_q = a_s + (size_t)q * c.P_alloc * 16;
+            const int n_ph = c.nph_y * c.nph_x;
+            const int all_items = n_ph * items;
+            constexpr int U = 4;
+            for (int j0 = tid; j0 < all_items; j0 += kProducerThreads * U) {
+              uint4 raw[U];
+              int pos[U];
+              bool ok[U];
 #pragma unroll
-                for (int k = 0; k < U; ++k) {
-                  const int j = j0 + k * kProducerThreads;
-                  const int pp = j >> qshift;
-                  pos[k] = (j < items) ? pp : -1;
-                  const int r = (int)__umulhi((unsigned)pp, c.pitch_magic);
-                  const int xp = pp - r * c.pitch;
-                  const int y_in = c.sy * (y0 + r - c.lead_y) + phy;
-                  const int x_in = c.sx * (xp - c.lead_x) + phx;
-                  ok[k] = (j < items) && y_in >= 0 && y_in < Hin && x_in >= 0 && x_in < Win;
-                  raw[k] = make_uint4(0u, 0u, 0u, 0u);
-                  if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(plane + ((size_t)y_in * Win + x_in) * a.src_cs + ch0));
-                }
+              for (int k = 0; k < U; ++k) {
+                const int jg = j0 + k * kProducerThreads;
+                const int ph = (jg >= items) + (jg >= 2 * items) + (jg >= 3 * items);   // n_ph <= 4
+                const int j = jg - ph * items;
+                const int phy = ph >> (c.nph_x - 1), phx = ph & (c.nph_x - 1);          // nph_x is 1 or 2
+                const int pp = j >> qshift;
+                pos[k] = (jg < all_items) ? ph * c.P_plane + pp : -1;
+                const int r = (int)__umulhi((unsigned)pp, c.pitch_magic);
+                const int xp = pp - r * c.pitch;
+                const int y_in = c.sy * (y0 + r - c.lead_y) + phy;
+                const int x_in = c.sx * (xp - c.lead_x) + phx;
+                ok[k] = (jg < all_items) && y_in >= 0 && y_in < Hin && x_in >= 0 && x_in < Win;
+                raw[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(plane + ((size_t)y_in * Win + x_in) * a.src_cs + ch0));
+              }
 #pragma unroll
-                for (int k = 0; k < U; ++k) {
-                  if (pos[k] < 0) continue;
-                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                  if (ok[k]) {
-                    o = xform8_h2(raw[k], s2, t2, l2);
-                  }
-                  *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
+              for (int k = 0; k < U; ++k) {
+                if (pos[k] < 0) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[k]) {
+                  o = xform8_h2(raw[k], s2, t2, l2);
                 }
+                *reinterpret_cast<uint4*>(a_q + (size_t)pos[k] * 16) = o;
               }
             }
           }
@@ -594,6 +602,16 @@ int launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  static const bool show_plan = getenv("FNNU_SHOW_PLAN") != nullptr;   // debugging aid: one line per launch
+  if (show_plan) {
+    const UmmaCfg& c = p.c;
+    fprintf(stderr,
+            "conv_umma: cin=%d cout=%d k=%dx%dx%d s=%d%d%d in=%dx%dx%d batch=%d%s | Nc=%d chunks=%d KC=%d G=%d TY=%d yblocks=%d T=%d "
+            "rows_mode=%d pitch=%d R=%d P_plane=%d stages=%d a_stage=%d b_stage=%d tmem_bufs=%d units=%d smem=%d\n",
+            a.cin, a.cout, a.k[0], a.k[1], a.k[2], a.s[0], a.s[1], a.s[2], a.in_d[0], a.in_d[1], a.in_d[2], a.batch,
+            a.transposed ? " transposed" : "", c.Nc, c.n_chunks, c.KC, c.G, c.TY, c.n_yblocks, c.T, c.rows_mode, c.pitch, c.R,
+            c.P_plane, c.stages, c.a_stage_bytes, c.b_stage_bytes, c.tmem_bufs, p.n_units, c.smem_bytes);
+  }
   conv_umma_kernel<<<grid, kThreadsUmma, p.c.smem_bytes, s>>>(p);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;

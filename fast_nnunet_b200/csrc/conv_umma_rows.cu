@@ -106,6 +106,19 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   return true;
 }
 
+// The 3 * CHUNKS MMAs of one kz plane of a row; descriptor offsets (16-byte units) are template constants.
+template <int CP, int CHUNKS, int KZ, int I>   // I -> (kx = I / CHUNKS, kc = I % CHUNKS)
+__device__ __forceinline__ void rows_issue_plane(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t& accum) {
+  if constexpr (I < 3 * CHUNKS) {
+    constexpr int kx = I / CHUNKS, kc = I % CHUNKS;
+    constexpr uint32_t a_off = (uint32_t)((KZ * 2 * CHUNKS + kc * 2) * 140 + kx);       // plan_rows: P_row == 140
+    constexpr uint32_t b_off = (uint32_t)((((KZ * 3 + kx) * CHUNKS + kc) * 2) * (3 * CP));
+    umma_f16_off<a_off, b_off>(d, da, db, idesc, accum);
+    accum = 1;
+    rows_issue_plane<CP, CHUNKS, KZ, I + 1>(d, da, db, idesc, accum);
+  }
+}
+
 template <int CP, int CHUNKS, int OCC>   // cout_pad (16 | 32); CHUNKS = Cin / 16; OCC = CTAs per SM
 __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const __grid_constant__ RowsArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -327,22 +340,9 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
         if (elect_one()) {
           const uint64_t da_st = (a_desc0 & 0xffffffff00000000ull) | da_lo;
           uint32_t accum = 0;
-#pragma unroll
-          for (int kz = 0; kz < 3; ++kz) {
-            if (!kzv[kz]) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-              for (int kc = 0; kc < CHUNKS; ++kc) {
-                constexpr uint32_t dummy = 0;
-                (void)dummy;
-                const uint32_t a_off = (uint32_t)((kz * (int)kQ + kc * 2) * (int)kProw + kx);
-                const uint32_t b_off = (uint32_t)((((kz * 3 + kx) * CHUNKS + kc) * 2) * (int)kNf);
-                umma_f16(d, da_st + a_off, b_desc0 + b_off, idesc, accum);
-                accum = 1;
-              }
-            }
-          }
+          if (kzv[0]) rows_issue_plane<CP, CHUNKS, 0, 0>(d, da_st, b_desc0, idesc, accum);
+          if (kzv[1]) rows_issue_plane<CP, CHUNKS, 1, 0>(d, da_st, b_desc0, idesc, accum);
+          if (kzv[2]) rows_issue_plane<CP, CHUNKS, 2, 0>(d, da_st, b_desc0, idesc, accum);
           umma_commit(&empty_bar[stage]);
           umma_commit(&tfull_bar[slot]);
         }

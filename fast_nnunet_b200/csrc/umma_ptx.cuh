@@ -65,6 +65,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with compile-time offsets added to both descriptors INSIDE the asm block: the front end cannot hoist
+// "base + constant" out of the issuing loop into one live 64-bit register per MMA (the 40-register MMA warp spilled 18
+// weight descriptors to local memory); ptxas turns each add into one UIADD3.64 on the uniform datapath.
+template <uint32_t kAOff, uint32_t kBOff>
+__device__ __forceinline__ void umma_f16_off(uint32_t tmem_d, uint64_t da_base, uint64_t db_base, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\tadd.u64 ta, %1, %5;\n\tadd.u64 tb, %2, %6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da_base), "l"(db_base), "r"(idesc), "r"(accumulate), "n"(kAOff), "n"(kBOff)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
