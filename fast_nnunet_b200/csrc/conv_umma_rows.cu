@@ -191,8 +191,15 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     constexpr int kQ_ = 2 * CHUNKS;
     constexpr int XP_STEP = kGroupThreads / kQ_;              // 32 positions per step
     constexpr int N_IT = (140 + XP_STEP - 1) / XP_STEP;       // 5
-    const int q = gt & (kQ_ - 1);
-    const int xp0 = gt / kQ_;
+    // A warp covers 16 positions x one PAIR of channel groups (32 contiguous bytes per voxel: full sectors), so
+    // whether a warp's channels carry a pending transform is warp-uniform: the up-sampled half of a decoder concat
+    // (ConvTranspose3d output, no norm) skips the in-place normalise pass altogether.
+    const int wg = gt >> 5;                                   // warp inside the group (1 or 2 q-pairs x 2 halves)
+    const int q = 2 * (wg & (CHUNKS - 1)) + (lane & 1);
+    const int xp0 = (wg / CHUNKS) * 16 + (lane >> 1);
+    bool q_identity = true;                                   // all 16 channels of the warp's q-pair: eps < 0
+#pragma unroll
+    for (int e = 0; e < 16; ++e) q_identity = q_identity && (a.src_meta[(q & ~1) * 8 + e].eps < 0.f);
     uint32_t goff[N_IT];                                      // byte offset of the voxel within its row
     uint32_t live = 0, inimg = 0;                             // bit it: position exists / lies inside the image
 #pragma unroll
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(kRowsThreads, OCC) conv_umma_rows_kernel(const
     auto finish_pending = [&](int keep_in_flight) {
       if (pend_stage < 0) return;
       if (keep_in_flight) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-      if (pend_row_ok) {
+      if (pend_row_ok && !q_identity) {
         uint8_t* st = ring + (size_t)pend_stage * c.stage_bytes + my_off;
 #pragma unroll
         for (int kz = 0; kz < 3; ++kz) {
