@@ -20,6 +20,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   while (!done) {
@@ -40,6 +51,7 @@ struct Params {
   int spin_warps;                        // warps polling an mbarrier that never completes (like idle pipeline roles)
   int random_data;                       // fill the operands with pseudo-random fp16 instead of zeros
   int issuers;                           // 1, 2 or 4 warps issue concurrently (own TMEM tiles)
+  int waits;                             // try_wait on an already-completed mbarrier before every group (0..4)
 };
 
 template <int PG, bool ELECT>
@@ -48,6 +60,7 @@ __global__ void __launch_bounds__(1024) rate_kernel(Params p, long long* out) {
   __shared__ uint64_t bar[4];
   __shared__ uint64_t side_bar[2];
   __shared__ uint64_t never_bar;
+  __shared__ uint64_t done_bar;   // phase 0 already complete
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int stop;
   const int warp = threadIdx.x >> 5;
@@ -61,6 +74,8 @@ __global__ void __launch_bounds__(1024) rate_kernel(Params p, long long* out) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&side_bar[0])), "r"(1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&side_bar[1])), "r"(1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&never_bar)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&done_bar)), "r"(1));
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   for (int i = threadIdx.x; i < 220 * 1024 / 16; i += blockDim.x) {
@@ -101,6 +116,10 @@ __global__ void __launch_bounds__(1024) rate_kernel(Params p, long long* out) {
     for (int r = 0; r < p.reps; ++r) {
       const uint32_t d = tmem + (uint32_t)(warp * slots + slot) * p.N;
       if (++slot == slots) slot = 0;
+      for (int w = 0; w < (p.waits & 7); ++w) {
+        if (p.waits & 8) mbar_wait_relaxed(smem_u32(&done_bar), 0); else mbar_wait(smem_u32(&done_bar), 0);
+      }
+      if (p.waits) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int t = 0; t < PG; ++t) {
         const uint64_t da = make_desc(a0 + (uint32_t)(t / 3) * 3 * p.a_tap_stride * 64 + (uint32_t)(t % 3) * p.a_tap_stride, p.a_lbo, p.a_sbo, p.layout);
@@ -188,22 +207,22 @@ static void run(const char* name, Params p, bool elect = false) {
 int main() {
   const int reps = 2000;
   // planar SWIZZLE_NONE, as conv_umma_rows.cu: LBO = plane stride 140 positions * 16 B, SBO = 128 B, tap shift 16 B
-  for (int N : {16, 48, 96, 128, 256}) run("planar none lbo=2240", Params{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1});
-  run("planar none lbo=2240, same tile", Params{128, 48, reps, 0, 0, 2240, 128, 16, 1, 0, 9, 0, 0, 1});
-  run("planar none lbo=2048", Params{128, 48, reps, 0, 0, 2048, 128, 16, 0, 0, 9, 0, 0, 1});
-  run("planar none lbo=2304 (18*128)", Params{128, 48, reps, 0, 0, 2304, 128, 16, 0, 0, 9, 0, 0, 1});
-  run("planar none lbo=2112 (2048+64)", Params{128, 48, reps, 0, 0, 2112, 128, 16, 0, 0, 9, 0, 0, 1});
-  run("planar none lbo=2176 (17*128)", Params{128, 48, reps, 0, 0, 2176, 128, 16, 0, 0, 9, 0, 0, 1});
-  run("planar none, tap shift 128 B", Params{128, 48, reps, 0, 0, 2240, 128, 128, 0, 0, 9, 0, 0, 1});
-  run("planar none, tap shift 0", Params{128, 48, reps, 0, 0, 2240, 128, 0, 0, 0, 9, 0, 0, 1});
-  run("none, K-chunks adjacent (lbo=128,sbo=256)", Params{128, 48, reps, 0, 0, 128, 256, 32, 0, 0, 9, 0, 0, 1});
-  run("swizzle 32B (sbo=256)", Params{128, 48, reps, 0, 6, 16, 256, 32, 0, 0, 9, 0, 0, 1});
-  run("swizzle 128B (sbo=1024)", Params{128, 48, reps, 0, 2, 16, 1024, 32, 0, 0, 9, 0, 0, 1});
-  run("M=64 planar none", Params{64, 48, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1});
-  for (int nw : {4, 8, 16}) run("planar none + smem noise", Params{128, 48, reps, nw, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1});
-  for (int nw : {8, 16}) run("planar none N=96 + smem noise", Params{128, 96, reps, nw, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1});
+  for (int N : {16, 48, 96, 128, 256}) run("planar none lbo=2240", Params{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none lbo=2240, same tile", Params{128, 48, reps, 0, 0, 2240, 128, 16, 1, 0, 9, 0, 0, 1, 0});
+  run("planar none lbo=2048", Params{128, 48, reps, 0, 0, 2048, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none lbo=2304 (18*128)", Params{128, 48, reps, 0, 0, 2304, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none lbo=2112 (2048+64)", Params{128, 48, reps, 0, 0, 2112, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none lbo=2176 (17*128)", Params{128, 48, reps, 0, 0, 2176, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none, tap shift 128 B", Params{128, 48, reps, 0, 0, 2240, 128, 128, 0, 0, 9, 0, 0, 1, 0});
+  run("planar none, tap shift 0", Params{128, 48, reps, 0, 0, 2240, 128, 0, 0, 0, 9, 0, 0, 1, 0});
+  run("none, K-chunks adjacent (lbo=128,sbo=256)", Params{128, 48, reps, 0, 0, 128, 256, 32, 0, 0, 9, 0, 0, 1, 0});
+  run("swizzle 32B (sbo=256)", Params{128, 48, reps, 0, 6, 16, 256, 32, 0, 0, 9, 0, 0, 1, 0});
+  run("swizzle 128B (sbo=1024)", Params{128, 48, reps, 0, 2, 16, 1024, 32, 0, 0, 9, 0, 0, 1, 0});
+  run("M=64 planar none", Params{64, 48, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  for (int nw : {4, 8, 16}) run("planar none + smem noise", Params{128, 48, reps, nw, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1, 0});
+  for (int nw : {8, 16}) run("planar none N=96 + smem noise", Params{128, 96, reps, nw, 0, 2240, 128, 16, 0, 0, 9, 0, 0, 1, 0});
   for (int cm : {1, 2}) {
-    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, cm, 9, 0, 0, 1};
+    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, cm, 9, 0, 0, 1, 0};
     run(cm == 1 ? "9 MMAs + 1 commit per group" : "9 MMAs + 2 commits per group", q);
     q.per_group = 1;
     run(cm == 1 ? "1 MMA + 1 commit per group" : "1 MMA + 2 commits per group", q);
@@ -211,7 +230,7 @@ int main() {
     run(cm == 1 ? "3 MMAs + 1 commit per group" : "3 MMAs + 2 commits per group", q);
   }
   for (int sw : {4, 12, 20}) {
-    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, 2, 9, sw, 0, 1};
+    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, 2, 9, sw, 0, 1, 0};
     char name[64];
     snprintf(name, sizeof(name), "9 MMAs + 2 commits, %d warps polling", sw);
     run(name, q);
@@ -220,25 +239,31 @@ int main() {
     run(name, q);
   }
   for (int N : {48, 96, 256}) {
-    Params q{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 1, 1};
+    Params q{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 1, 1, 0};
     run("random operands, no commit", q);
     q.commits = 2;
     run("random operands, 2 commits per group", q);
   }
   for (int N : {16, 48, 96}) {
     for (int iss : {1, 2, 4}) {
-      Params q{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 1, iss};
+      Params q{128, N, reps, 0, 0, 2240, 128, 16, 0, 0, 9, 0, 1, iss, 0};
       run("concurrent issuers", q, false);
       run("concurrent issuers", q, true);
     }
   }
   {
-    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, 2, 9, 0, 1, 1};
+    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, 2, 9, 0, 1, 1, 0};
     run("2 commits per 9 MMAs", q, true);
     q.commits = 1;
     run("1 commit per 9 MMAs", q, true);
     q.issuers = 2;
     run("1 commit per 9 MMAs", q, true);
+  }
+  for (int w : {0, 1, 2, 4, 9, 10}) {
+    Params q{128, 48, reps, 0, 0, 2240, 128, 16, 0, 2, 9, 0, 1, 1, w};
+    char name[64];
+    snprintf(name, sizeof(name), "9 MMAs + 2 commits + %d %s waits", w & 7, (w & 8) ? "relaxed" : "acquire");
+    run(name, q, true);
   }
   return 0;
 }
