@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     const uint32_t a_lbo = (uint32_t)c.P_alloc * 16, b_lbo = (uint32_t)c.Nc * 16;
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128);
     const uint64_t b_desc0 = make_desc(0, b_lbo, 128);
+    const uint64_t desc_hi_a = a_desc0 & 0xffffffff00000000ull, desc_hi_b = b_desc0 & 0xffffffff00000000ull;
     // tile bases: flat mode i*128; one tile per row (W == 128) i*pitch; several tiles per row: nested
     const bool nested = c.rows_mode && c.tiles_per_row > 1;
     const int n_outer = nested ? c.TY : 1;
@@ -387,25 +388,27 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           const uint32_t a_base = smem_u32(ring + (size_t)stage * stage_bytes);
           const uint32_t b_base = a_base + (uint32_t)c.a_stage_bytes;
           if (elect_one()) {
+          // Descriptor arithmetic on the LOW word only: the 14-bit start-address field never carries into the LBO
+          // field (shared memory < 256 KB), so each MMA costs one 32-bit uniform add per operand instead of a 64-bit
+          // add-with-carry chain (the issue loop, not the tensor pipe, paced layers with few tiles per tap).
+          const uint32_t a_lo0 = (uint32_t)a_desc0 + (a_base >> 4), b_lo0 = (uint32_t)b_desc0 + (b_base >> 4);
           for (int kc = 0; kc < c.KC; ++kc) {
             for (int t = 0; t < c.ntyx; ++t) {
-              const uint64_t db = b_desc0 + (uint64_t)((b_base + (uint32_t)((kc * c.ntyx + t) * 2) * b_lbo) >> 4);
-              const uint64_t da0 = a_desc0 + (uint64_t)((a_base + (uint32_t)(kc * 2) * a_lbo + (uint32_t)c.tap_aoff[t] * 16) >> 4);
+              const uint64_t db = desc_hi_b | (uint64_t)(b_lo0 + (uint32_t)((kc * c.ntyx + t) * 2) * (b_lbo >> 4));
+              const uint32_t da_lo0 = a_lo0 + (uint32_t)(kc * 2) * (a_lbo >> 4) + (uint32_t)c.tap_aoff[t];
               const uint32_t accum = (first && kc == 0 && t == 0) ? 0u : 1u;
               // tile i of the unit sits at row (i / tiles_per_row), column block (i % tiles_per_row): pure
               // uniform-register arithmetic per MMA (no memory reads on the issue path)
               uint32_t d = d_base;
-              uint64_t da_row = da0;
+              uint32_t da_row = da_lo0;
               for (int r = 0; r < n_outer; ++r) {
-                uint64_t da = da_row;
 #pragma unroll 4
                 for (int j = 0; j < n_inner; ++j) {
-                  umma_f16(d, da, db, idesc, accum);
-                  d += (uint32_t)c.Nc;
-                  da += inner_step;
+                  umma_f16(d_base + (uint32_t)((r * n_inner + j) * c.Nc), desc_hi_a | (uint64_t)(da_row + (uint32_t)j * inner_step), db, idesc, accum);
                 }
-                da_row += (uint64_t)outer_step;
+                da_row += outer_step;
               }
+              (void)d;
             }
           }
           umma_commit(&empty_bar[stage]);
