@@ -25,9 +25,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# ncu --set full on conv_umma_rows_kernel<16,1> (profiles/r01_ncu_prof_rows16d.txt): dram read 545 MB + write 510 MB
-# for 537 + 537 MB algorithmic -> measured DRAM traffic / algorithmic bytes
-NCU_TRAFFIC_OVER_ALGORITHMIC = (545.4 + 510.2) / (536.9 + 536.9)
+# ncu --set full on the dominant launch, conv_umma_rows_kernel<16,2> = dec5.0 with 32 patches
+# (profiles/r01_ncu_final_rows_dec5.txt): dram read 5.054 GB + write 2.125 GB for 4.295 + 2.147 GB algorithmic
+# -> measured DRAM traffic / algorithmic bytes (the 18 % extra reads are z-neighbour planes that missed L2)
+NCU_TRAFFIC_OVER_ALGORITHMIC = (5.0535 + 2.1254) / (4.2950 + 2.1475)
+# bounded CPU samples: ~3.3 s per 128^3 student tile x 8 passes on 16 cores
+CPU_BASELINE_TILES = 4      # cpu_baseline of our arm: ~13 s of CPU work
+REF_TILES_PER_STEP = 3      # --impl reference: ~10 s per step
 STUDENT_FEATS = [16, 32, 64, 128, 160, 160]
 TEACHER_FEATS = [32, 64, 128, 256, 320, 320]
 ISO_K = [[3, 3, 3]] * 6
@@ -169,12 +173,12 @@ def run_reference(args, wl):
     cores = os.cpu_count() or 1
     times = []
     for i in range(args.warmup + args.steps):
-        spv, dt, n_total = cpu_reference_sample(wl, 1, cores)
+        spv, dt, n_total = cpu_reference_sample(wl, REF_TILES_PER_STEP, cores)
         if i >= args.warmup:
             times.append(spv)
     spv = float(np.mean(times))
     value = nvox / spv / 1e6
-    sample = f'1 of {n_total} tiles x 8 mirror passes per step (oracle port of the reference CPU path, fp32 network, ' \
+    sample = f'{REF_TILES_PER_STEP} of {n_total} tiles x 8 mirror passes per step (oracle port of the reference CPU path, fp32 network, ' \
              f'fp16 accumulators), extrapolated by tile count'
     line = {
         'impl': 'reference', 'metric': 'sliding-window inference throughput', 'value': value, 'unit': 'Mvoxel/s',
@@ -320,10 +324,11 @@ def run_ours(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            spv, dt, n_total = cpu_reference_sample(wl, 1, cores)
+            spv, dt, n_total = cpu_reference_sample(wl, CPU_BASELINE_TILES, cores)
             cpu = {'value': nvox / spv / 1e6, 'unit': 'Mvoxel/s', 'cores': cores, 'kind': 'port',
                    'sec_per_volume': spv,
-                   'sample': f'1 of {n_total} tiles x 8 mirror passes ({dt:.1f} s of CPU work), extrapolated by tile count'}
+                   'sample': f'{CPU_BASELINE_TILES} of {n_total} tiles x 8 mirror passes ({dt:.1f} s of CPU work), '
+                             f'extrapolated by tile count'}
         line = {
             'metric': 'sliding-window inference throughput', 'value': nvox / (ms * 1e-3) / 1e6, 'unit': 'Mvoxel/s',
             'sec_per_volume': ms * 1e-3, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
