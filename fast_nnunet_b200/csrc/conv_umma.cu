@@ -54,6 +54,10 @@ struct UmmaCfg {
   int nkz, pz, sz, sy, sx;
   int ntyx;
   int tap_aoff[9];        // per in-plane tap: phase * P_plane + shifted start (positions)
+  // descriptor offsets (16-byte units) of the (kc, tap) operand pair inside a stage, in issue order: .x for A, .y for
+  // B.  Read with one uniform constant load per tap; computing them in the issue loop cost ~20 dependent uniform
+  // instructions per tap, which paced every layer with 1-3 M-tiles per tap.
+  uint2 tap_desc[36];     // KC <= 4, ntyx <= 9
   int stages, a_stage_bytes, b_stage_bytes;
   int tmem_bufs;
   int smem_bytes;
@@ -195,6 +199,11 @@ static bool plan_umma(const ConvArgs& a, UmmaCfg& c) {
   c.b_stage_bytes = c.KC * c.ntyx * 2 * c.Nc * 16;
   c.smem_bytes = c.stages * (c.a_stage_bytes + c.b_stage_bytes) + misc;
   c.pitch_magic = (unsigned)((0x100000000ull + (unsigned)c.pitch - 1) / (unsigned)c.pitch);
+  for (int kc = 0; kc < c.KC; ++kc)
+    for (int t = 0; t < c.ntyx; ++t) {
+      c.tap_desc[kc * c.ntyx + t].x = (unsigned)(kc * 2 * c.P_alloc + c.tap_aoff[t]);
+      c.tap_desc[kc * c.ntyx + t].y = (unsigned)((kc * c.ntyx + t) * 2 * c.Nc);
+    }
   if ((c.P_alloc * 16 >> 4) > 0x3FFF || (c.Nc * 16 >> 4) > 0x3FFF) return false;
   c.ok = 1;
   return true;
@@ -392,23 +401,21 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           // field (shared memory < 256 KB), so each MMA costs one 32-bit uniform add per operand instead of a 64-bit
           // add-with-carry chain (the issue loop, not the tensor pipe, paced layers with few tiles per tap).
           const uint32_t a_lo0 = (uint32_t)a_desc0 + (a_base >> 4), b_lo0 = (uint32_t)b_desc0 + (b_base >> 4);
-          for (int kc = 0; kc < c.KC; ++kc) {
-            for (int t = 0; t < c.ntyx; ++t) {
-              const uint64_t db = desc_hi_b | (uint64_t)(b_lo0 + (uint32_t)((kc * c.ntyx + t) * 2) * (b_lbo >> 4));
-              const uint32_t da_lo0 = a_lo0 + (uint32_t)(kc * 2) * (a_lbo >> 4) + (uint32_t)c.tap_aoff[t];
-              const uint32_t accum = (first && kc == 0 && t == 0) ? 0u : 1u;
-              // tile i of the unit sits at row (i / tiles_per_row), column block (i % tiles_per_row): pure
-              // uniform-register arithmetic per MMA (no memory reads on the issue path)
-              uint32_t d = d_base;
-              uint32_t da_row = da_lo0;
-              for (int r = 0; r < n_outer; ++r) {
+          const int n_taps = c.KC * c.ntyx;
+          for (int kt = 0; kt < n_taps; ++kt) {
+            const uint2 off = c.tap_desc[kt];
+            const uint64_t db = desc_hi_b | (uint64_t)(b_lo0 + off.y);
+            const uint32_t da_lo0 = a_lo0 + off.x;
+            const uint32_t accum = (first && kt == 0) ? 0u : 1u;
+            // tile i of the unit sits at row (i / tiles_per_row), column block (i % tiles_per_row): pure
+            // uniform-register arithmetic per MMA (no memory reads on the issue path)
+            uint32_t da_row = da_lo0;
+            for (int r = 0; r < n_outer; ++r) {
 #pragma unroll 4
-                for (int j = 0; j < n_inner; ++j) {
-                  umma_f16(d_base + (uint32_t)((r * n_inner + j) * c.Nc), desc_hi_a | (uint64_t)(da_row + (uint32_t)j * inner_step), db, idesc, accum);
-                }
-                da_row += outer_step;
+              for (int j = 0; j < n_inner; ++j) {
+                umma_f16(d_base + (uint32_t)((r * n_inner + j) * c.Nc), desc_hi_a | (uint64_t)(da_row + (uint32_t)j * inner_step), db, idesc, accum);
               }
-              (void)d;
+              da_row += outer_step;
             }
           }
           umma_commit(&empty_bar[stage]);
