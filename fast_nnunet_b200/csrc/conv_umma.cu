@@ -140,7 +140,7 @@ static bool plan_umma(const ConvArgs& a, UmmaCfg& c) {
   c.rows_mode = (c.Wo % 128 == 0);
   c.tiles_per_row = c.rows_mode ? c.Wo / 128 : 0;
   const int nph = c.nph_y * c.nph_x;
-  const int misc = 512 + 3 * a.cin * 4 + 2 * c.Nc * 4 + 1024;
+  const int misc = 512 + 3 * a.cin * 4 + 8 * c.Nc * 4 + (c.cout_virtual / 16) * 4 + a.cout_pad * 4 + 1024;
   const int avail = kSmemLimit - misc;
   const int center = c.lead_y * c.pitch + c.lead_x;
   int max_shift = 0;   // largest shifted start (relative to the tile base) over the taps
@@ -209,6 +209,21 @@ static bool plan_umma(const ConvArgs& a, UmmaCfg& c) {
   return true;
 }
 
+// v[0..15] per lane, 32 lanes: afterwards v[0] of lanes 2 i and 2 i + 1 holds the sum over the warp of value i.
+__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int n = 8, off = 16; n >= 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = hi ? v[i] : v[i + n];
+      const float keep = hi ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 struct UnitIdx {
   int b, z, yb, nc;
 };
@@ -238,7 +253,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
   float* xs = reinterpret_cast<float*>(tile_tab + 64);
   float* xh = xs + a.cin;
   float* xl = xh + a.cin;
-  float* stat_s = xl + a.cin;   // [2][Nc]
+  float* stat_s = xl + a.cin;                               // [4 epilogue warps][2][Nc] partial sums of one unit
+  float* bias_s = stat_s + 8 * c.Nc;                        // [cout_pad]
+  uint32_t* grp_tab = reinterpret_cast<uint32_t*>(bias_s + a.cout_pad);   // per 16-column group: co0 | tap offsets
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,7 +272,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * c.Nc; i += blockDim.x) stat_s[i] = 0.f;
+  for (int i = threadIdx.x; i < a.cout_pad; i += blockDim.x) bias_s[i] = (a.bias && i < a.cout) ? __ldg(a.bias + i) : 0.f;
+  for (int g = threadIdx.x; g < c.cout_virtual / 16; g += blockDim.x) {
+    // (virtual) output channel 16 g: real channel group and, for a transposed conv, the output offset of its tap
+    uint32_t e = (uint32_t)(g * 16);
+    if (c.transposed) {
+      const int tap = (g * 16) / a.cout_pad;
+      const int co0 = g * 16 - tap * a.cout_pad;
+      const int ddx = tap % a.s[2], ddy = (tap / a.s[2]) % a.s[1], ddz = tap / (a.s[2] * a.s[1]);
+      e = (uint32_t)co0 | ((uint32_t)ddz << 16) | ((uint32_t)ddy << 20) | ((uint32_t)ddx << 24);
+    }
+    grp_tab[g] = e;
+  }
   for (int i = threadIdx.x; i < c.T; i += blockDim.x) tile_tab[i] = (uint32_t)tile_base_of(c, i);
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
@@ -450,20 +478,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
       const uint32_t d_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(wq * 32) << 16);
       __half* out_b = a.dst + (size_t)ui.b * Dout * Hout * Wout * a.dst_cs;
       for (int n0 = 0; n0 < c.Nc; n0 += 16) {
-        const int v0 = ui.nc * c.Nc + n0;          // first (virtual) output channel of this 16-group
-        int co0 = v0, oz = ui.z, oy_off = 0, ox_off = 0, ys = 1, xsn = 1;
+        const uint32_t ge = grp_tab[(ui.nc * c.Nc + n0) >> 4];
+        const int co0 = (int)(ge & 0xffffu);
+        int oz = ui.z, oy_off = 0, ox_off = 0, ys = 1, xsn = 1;
         if (c.transposed) {
-          const int tap = v0 / a.cout_pad;
-          co0 = v0 - tap * a.cout_pad;
-          const int ddx = tap % a.s[2];
-          const int ddy = (tap / a.s[2]) % a.s[1];
-          const int ddz = tap / (a.s[2] * a.s[1]);
-          oz = ui.z * a.s[0] + ddz;
-          oy_off = ddy; ox_off = ddx; ys = a.s[1]; xsn = a.s[2];
+          oz = ui.z * a.s[0] + (int)((ge >> 16) & 15u);
+          oy_off = (int)((ge >> 20) & 15u); ox_off = (int)((ge >> 24) & 15u); ys = a.s[1]; xsn = a.s[2];
         }
         float bias[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bias[j] = (a.bias && co0 + j < a.cout) ? __ldg(a.bias + co0 + j) : 0.f;
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + co0 + j);
+          bias[j] = bv.x; bias[j + 1] = bv.y; bias[j + 2] = bv.z; bias[j + 3] = bv.w;
+        }
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
@@ -503,20 +530,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
           }
         }
         if (do_stats) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-              s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-              s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-            }
-          }
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              atomicAdd(&stat_s[n0 + j], s1[j]);
-              atomicAdd(&stat_s[c.Nc + n0 + j], s2[j]);
-            }
+          // 16 values x 32 lanes -> lane pair (2 i, 2 i + 1) ends up with the warp total of value i: each exchange step
+          // halves the values a lane keeps (16 shuffles per array instead of 80), and the totals go to this warp's own
+          // slots with plain stores (the shared-memory atomics of four warps on the same words were the slow part)
+          warp_transpose_reduce16(s1, lane);
+          warp_transpose_reduce16(s2, lane);
+          if (!(lane & 1)) {
+            float* slot = stat_s + (size_t)wq * 2 * c.Nc + n0 + (lane >> 1);
+            slot[0] = s1[0];
+            slot[c.Nc] = s2[0];
           }
         }
       }
@@ -528,8 +550,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         for (int i = et; i < 2 * c.Nc; i += kEpilogueThreads) {
           const int which = i / c.Nc, n = i - which * c.Nc;
           const int co = ui.nc * c.Nc + n;
-          if (co < a.cout) atomicAdd(a.dst_stats + ((size_t)ui.b * a.dst_stat_stride + co) * 2 + which, (double)stat_s[i]);
-          stat_s[i] = 0.f;
+          const float tot = (stat_s[i] + stat_s[2 * c.Nc + i]) + (stat_s[4 * c.Nc + i] + stat_s[6 * c.Nc + i]);
+          if (co < a.cout) atomicAdd(a.dst_stats + ((size_t)ui.b * a.dst_stat_stride + co) * 2 + which, (double)tot);
         }
         named_bar_sync(2, kEpilogueThreads);
       }
