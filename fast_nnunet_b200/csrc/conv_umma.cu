@@ -72,14 +72,14 @@ struct UmmaArgs {
 
 // Six warpgroups: 4 of producers (ncu: the producers are instruction-latency bound -- ~40 instructions per 16-byte
 // item at ~4.5 cycles each with 2 warps per scheduler -- so 16 warps instead of 8), 1 epilogue, 1 holding the MMA warp
-// (its 3 other warps only donate registers).  setmaxnreg: 512 x 88 + 128 x 88 + 128 x 40 = 768 x 80 registers (the producers
+// (its 3 other warps only donate registers).  setmaxnreg: 512 x 80 + 128 x 120 + 128 x 40 = 768 x 80 registers (the producers
 // keep U = 8 16-byte loads in flight per thread: the stride-2 layer was bound by memory-level parallelism).
 constexpr int kProducerWarps = 16;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kMmaWarp = kProducerWarps + 4;
 constexpr int kThreadsUmma = (kMmaWarp + 4) * 32;
-constexpr int kRegsProducerU = 88, kRegsMmaU = 40, kRegsEpilogueU = 88;   // must sum to <= 768 x 80: setmaxnreg moves registers inside the CTA's own allocation
+constexpr int kRegsProducerU = 80, kRegsMmaU = 40, kRegsEpilogueU = 120;   // must sum to <= 768 x 80: setmaxnreg moves registers inside the CTA's own allocation
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline int tile_base_of(const UmmaCfg& c, int i) {
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
 
   if (warp < kProducerWarps) {
     // =========================== PRODUCERS ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducerU));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducerU));
     const int tid = threadIdx.x;
     const int Q = 2 * c.KC;               // 8-channel groups per stage (2, 4 or 8)
     const int qshift = (Q == 2) ? 1 : (Q == 4 ? 2 : 3);
@@ -357,11 +357,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
               bool ok[U];
 #pragma unroll
               for (int k = 0; k < U; ++k) {
+                // item order (fastest first): channel group q, x phase, position, y phase -- consecutive lanes read
+                // consecutive global bytes even with stride 2 in x (per-phase order fetched every 64-byte L2 line twice)
                 const int jg = j0 + k * kProducerThreads;
-                const int ph = (jg >= items) + (jg >= 2 * items) + (jg >= 3 * items);   // n_ph <= 4
-                const int j = jg - ph * items;
-                const int phy = ph >> (c.nph_x - 1), phx = ph & (c.nph_x - 1);          // nph_x is 1 or 2
-                const int pp = j >> qshift;
+                const int idx = jg >> qshift;
+                const int phx = idx & (c.nph_x - 1);                                     // nph_x, nph_y are 1 or 2
+                const int t = idx >> (c.nph_x - 1);
+                const int phy = (t >= c.P_fill) ? 1 : 0;
+                const int pp = t - phy * c.P_fill;
+                const int ph = phy * c.nph_x + phx;
                 pos[k] = (jg < all_items) ? ph * c.P_plane + pp : -1;
                 const int r = (int)__umulhi((unsigned)pp, c.pitch_magic);
                 const int xp = pp - r * c.pitch;
@@ -496,14 +500,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
         for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
         const bool full16 = co0 + 16 <= a.cout;
         __half* out_plane = out_b + (size_t)oz * Hout * Wout * a.dst_cs;
-        for (int i = 0; i < c.T; ++i) {
+        // two tiles per TMEM round trip: the tcgen05.ld latency was exposed once per tile
+        auto emit_tile = [&](int i, const uint32_t (&acc)[16]) {
           const int pos = (int)tile_tab[i] + wq * 32 + lane;
           const int yo = (int)__umulhi((unsigned)pos, c.pitch_magic);
           const int xo = pos - yo * c.pitch;
           const int y = y0 + yo;
           const bool valid = xo < c.Wo && yo < c.TY && y < c.Ho;
-          uint32_t acc[16];
-          tmem_ld16(d_base + (uint32_t)(i * c.Nc + n0), acc);
           if (valid) {
             __half2 hv[8];
 #pragma unroll
@@ -528,6 +531,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) conv_umma_kernel(const __grid
                 if (co0 + j < a.cout) q[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
+        };
+        for (int i = 0; i < c.T; i += 2) {
+          uint32_t acc0[16], acc1[16];
+          const bool two = i + 1 < c.T;
+          tmem_ld16_nowait(d_base + (uint32_t)(i * c.Nc + n0), acc0);
+          if (two) tmem_ld16_nowait(d_base + (uint32_t)((i + 1) * c.Nc + n0), acc1);
+          tmem_wait_ld();
+          emit_tile(i, acc0);
+          if (two) emit_tile(i + 1, acc1);
         }
         if (do_stats) {
           // 16 values x 32 lanes -> lane pair (2 i, 2 i + 1) ends up with the warp total of value i: each exchange step
