@@ -26,9 +26,9 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 # ncu --set full on the dominant launch, conv_umma_rows_kernel<16,2> = dec5.0 with 32 patches
-# (profiles/r01_ncu_final_rows_dec5.txt): dram read 5.054 GB + write 2.125 GB for 4.295 + 2.147 GB algorithmic
+# (profiles/r01_ncu_final_rows_dec5.txt): dram read 5.070 GB + write 2.121 GB for 4.295 + 2.147 GB algorithmic
 # -> measured DRAM traffic / algorithmic bytes (the 18 % extra reads are z-neighbour planes that missed L2)
-NCU_TRAFFIC_OVER_ALGORITHMIC = (5.0535 + 2.1254) / (4.2950 + 2.1475)
+NCU_TRAFFIC_OVER_ALGORITHMIC = (5.0698 + 2.1215) / (4.2950 + 2.1475)
 # bounded CPU samples: ~3.3 s per 128^3 student tile x 8 passes on 16 cores
 CPU_BASELINE_TILES = 4      # cpu_baseline of our arm: ~13 s of CPU work
 REF_TILES_PER_STEP = 3      # --impl reference: ~10 s per step
