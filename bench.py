@@ -192,6 +192,15 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def _conv_kernel_name(dom):
+    """Which tcgen05 kernel the engine picks for a stride-1 3x3x3 conv (mirrors plan_rows in conv_umma_rows.cu): the
+    row-streaming kernel for Cin in {16, 32}, Cout <= 32 and 64 <= W <= 128, else the general implicit GEMM."""
+    cout_pad = (dom['cout'] + 15) // 16 * 16
+    w = dom['out_dims'][2]
+    rows = dom['cin'] in (16, 32) and cout_pad in (16, 32) and 64 <= w <= 128
+    return 'conv_umma_rows_kernel' if rows else 'conv_umma_kernel'
+
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -305,10 +314,11 @@ def run_ours(args, wl):
         # capture of the same kernel class (profiles/README.md), scaled to this launch's patch count
         roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': peaks['bf16_tflops_sustained'],
                 'achieved': dom['flop_per_launch'] / (dom['ms'] * 1e-3) / 1e12,
-                'traffic': dom['algorithmic_bytes_per_launch'] * NCU_TRAFFIC_OVER_ALGORITHMIC,
+                'traffic': (dom['algorithmic_bytes_per_launch'] * NCU_TRAFFIC_OVER_ALGORITHMIC
+                            if _conv_kernel_name(dom) == 'conv_umma_rows_kernel' else None),
                 'algorithmic_bytes': dom['algorithmic_bytes_per_launch'],
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; fp16 runs at the same tcgen05 rate)',
-                'kernel': 'conv_umma_rows_kernel (' + dom['op'] + f", Conv3d {dom['cin']}->{dom['cout']} @{dom['out_dims']}"
+                'kernel': _conv_kernel_name(dom) + ' (' + dom['op'] + f", Conv3d {dom['cin']}->{dom['cout']} @{dom['out_dims']}"
                           f", {dom['patches_per_launch']} patches per launch)",
                 'ms_per_launch': dom['ms'], 'flop_per_launch': dom['flop_per_launch']}
         roof['frac'] = roof['achieved'] / roof['peak']
