@@ -80,17 +80,12 @@ static bool plan_rows(const ConvArgs& a, RowsCfg& c) {
   c.w_bytes = c.nkz * c.nkx * c.chunks * 2 * c.Nf * 16;
   if (c.w_bytes > 80 * 1024) return false;
   const int misc = 1024 + 3 * a.cin * 4 + 1024;
-  // Two CTAs per SM (256 TMEM columns and ~113 KB of shared memory each) were measured SLOWER (enc0.1: 2.8 -> 4.0 ms
-  // per 32 patches): the kernel is bound by shared-memory traffic (A is re-read for each of the 9 taps), not by
-  // latency, so the variant stays compiled but is not selected.
-  c.occ = 2;
-  if (true) c.occ = 1;
-  int st = (kRowsSmemLimit / c.occ - misc - c.w_bytes) / c.stage_bytes;
-  // stages > producer groups is required: a group publishes row r only while it prefetches row r + 4
-  if (st <= rows_groups(c.chunks) || 256 / c.Nf < 4) {
-    c.occ = 1;
-    st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
-  }
+  // One CTA per SM.  Two (256 TMEM columns and ~113 KB of shared memory each) were measured SLOWER (enc0.1: 2.8 ->
+  // 4.0 ms per 32 patches): the kernel is bound by shared-memory traffic (A is re-read for each of the 9 taps), not
+  // by latency.  The OCC template parameter is kept for that experiment.
+  c.occ = 1;
+  const int st = (kRowsSmemLimit - misc - c.w_bytes) / c.stage_bytes;
+  // stages > producer groups is required: a group publishes row r only while it prefetches row r + groups
   if (st <= rows_groups(c.chunks)) return false;
   c.stages = st > kRowsMaxStages ? kRowsMaxStages : st;
   c.tmem_cols = c.occ == 2 ? 256 : 512;
@@ -544,9 +539,7 @@ int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
     }                                                                                                                \
     conv_umma_rows_kernel<CPV, CHV, OCCV><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);                                   \
   }
-  FNNU_ROWS_CASE(16, 1, 2)
-  else FNNU_ROWS_CASE(16, 2, 2)
-  else FNNU_ROWS_CASE(16, 1, 1)
+  FNNU_ROWS_CASE(16, 1, 1)
   else FNNU_ROWS_CASE(16, 2, 1)
   else FNNU_ROWS_CASE(32, 1, 1)
   else FNNU_ROWS_CASE(32, 2, 1)
