@@ -11,14 +11,15 @@
 // Shared-memory operand layout (no swizzle, K-major canonical layout of the UMMA descriptor):
 //   A stage : [8-channel group q][position p][8 halves]   -> row pitch 16 B, SBO = 128 B, LBO = plane
 //   B stage : [chunk][tap][8-channel group][cout n][8 halves]
-// A is written by 8 producer warps that read the RAW fp16 output of the previous layer from HBM/L2 and
+// A is written by 16 producer warps that read the RAW fp16 output of the previous layer from HBM/L2 and
 // apply its InstanceNorm affine + LeakyReLU on the way (the fused "normalise on load"); B (weights,
 // pre-packed per stage) arrives by one cp.async.bulk (TMA engine) per stage.  One thread issues the
 // MMAs; 4 epilogue warps drain TMEM (tcgen05.ld), add the bias, round to fp16, store channels-last and
 // accumulate the InstanceNorm sums of the rounded values (fp32 partials -> fp64 atomics).
 //
-// Warp roles (416 threads): warps 0-7 producers, warps 8-11 epilogue (TMEM lane quarter = warp % 4),
-// warp 12 MMA issuer + TMEM allocator.  Pipelines: smem ring (full/empty mbarriers) between producers
+// Warp roles (768 threads, setmaxnreg 80 / 120 / 40): warps 0-15 producers, warps 16-19 epilogue (TMEM lane quarter
+// = warp % 4), warp 20 MMA issuer (elect.sync) + TMEM allocator, warps 21-23 only donate registers.
+// Pipelines: smem ring (full/empty mbarriers) between producers
 // and MMA; TMEM accumulator buffers (full/empty mbarriers) between MMA and epilogue.
 //
 // Strided convolutions keep the same structure through a phase decomposition: with stride s the tap k

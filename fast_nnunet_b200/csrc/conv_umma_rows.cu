@@ -1,10 +1,10 @@
 // Row-streaming tcgen05 convolution for the thin, full-resolution layers (Cout <= 32, W <= 128 ...):
 // the layers that hold most of a nnU-Net's FLOPs (48 % at 128^3 with Cout = 16).
 //
-// Why a second kernel.  With A read from shared memory a 128 x N x 16 tcgen05.mma costs ~64 cycles of
-// operand fetch (4 KB of A at 64 B/clk, measured: tc pipe busy 53 %, tensor math 6 % on the generic
-// kernel) no matter how small N is; its math takes only N/2 cycles.  A 3x3x3 conv with Cout = 16 issued
-// as 27 taps x (N = 16) is therefore operand-fetch bound at <= 12 % of the tensor peak.  Here the ky taps
+// Why a second kernel.  With A and B read from shared memory a 128 x N x 16 tcgen05.mma takes 39 / 44 / 56 / 64 /
+// 128 cycles for N = 16 / 48 / 96 / 128 / 256 (tests/cuda/bench_umma_rate.cu): below N = 128 it is bound by the
+// operand fetch (4 KB of A + 32 N bytes of B at ~125 B/cycle), its math takes only N/2 cycles.  A 3x3x3 conv with
+// Cout = 16 issued as 27 taps x (N = 16) is therefore operand-fetch bound at <= 12 % of the tensor peak.  Here the ky taps
 // are FOLDED INTO N:   D'[row r][x, (ky, co)] = sum_{kz, kx, ci} X[z + kz - 1, r, x + kx - 1, ci] * W[kz, ky, kx][ci, co]
 // is one accumulator tile per INPUT row r (N = 3 * Cout, 9 MMAs per 16 input channels instead of 27), and
 //   out[y][x, co] = D'[y - 1][x, (2, co)] + D'[y][x, (1, co)] + D'[y + 1][x, (0, co)]
@@ -45,7 +45,8 @@ struct RowsArgs {
 
 // 16 producer warps (the producers are latency-bound: ncu shows them busy ~85 % at one instruction per ~8 cycles
 // per warp), dealt in groups of 64 * CHUNKS threads (8 groups for Cin 16, 4 groups for Cin 32) so that a thread
-// always covers a row in 5 steps of 32 positions.  Warps 16-19: epilogue, warp 20: MMA.
+// always covers a row in 5 steps of 32 positions.  Warps 16-19: epilogue, warp 20: MMA (one thread chosen with
+// elect.sync issues; the other lanes only take part in the mbarrier waits).
 constexpr int kRowsProducerWarps = 16;
 constexpr int kRowsProducerThreads = kRowsProducerWarps * 32;
 constexpr int kRowsMmaWarp = kRowsProducerWarps + 4;
