@@ -31,7 +31,7 @@ import torch  # noqa: E402
 NCU_TRAFFIC_OVER_ALGORITHMIC = (5.0698 + 2.1215) / (4.2950 + 2.1475)
 # bounded CPU samples: ~3.3 s per 128^3 student tile x 8 passes on 16 cores
 CPU_BASELINE_TILES = 4      # cpu_baseline of our arm: ~13 s of CPU work
-REF_TILES_PER_STEP = 3      # --impl reference: ~10 s per step
+REF_TILES_PER_STEP = int(os.environ.get('FNNU_BENCH_REF_TILES', '3'))   # --impl reference: ~10 s per step
 STUDENT_FEATS = [16, 32, 64, 128, 160, 160]
 TEACHER_FEATS = [32, 64, 128, 256, 320, 320]
 ISO_K = [[3, 3, 3]] * 6
