@@ -13,6 +13,7 @@
 //   * the output is written RAW (conv + bias, rounded to fp16) and the per-(sample, channel) sum and
 //     sum of squares of the ROUNDED values are accumulated in fp64 for the consumer.
 #include <type_traits>
+#include <cstdlib>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -479,6 +480,9 @@ int launch_conv_specialised(const ConvArgs& a, cudaStream_t s) {
     return FNNU_OK;
   }
   if (small_cin_ok(a)) {
+    // Cin == 1 first layers run on the tensor cores (conv_first_umma.cu); FNNU_FIRST_LAYER_TC=0 selects the CUDA-core kernel
+    static const bool first_tc = [] { const char* e = getenv("FNNU_FIRST_LAYER_TC"); return !(e && e[0] == '0'); }();
+    if (first_tc && first_umma_supported(a)) return launch_conv_first_umma(a, s);
     long long groups = (long long)a.out_d[0] * a.out_d[1] * ((a.out_d[2] + 3) / 4);
     dim3 grid((unsigned)((groups + 127) / 128), (unsigned)(a.cout_pad / 16), (unsigned)a.batch);
     size_t smem = (size_t)(a.ntaps * a.cin * 16 + 4 * 32) * sizeof(float);

@@ -71,4 +71,8 @@ bool rows_supported(const ConvArgs& a);
 int launch_pack_weights_rows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_rows(const ConvArgs& a, cudaStream_t s);
 
+// conv_first_umma.cu: Cin == 1 first layer with the taps as the K dimension of the MMA (FNNU_FIRST_LAYER_TC=1)
+bool first_umma_supported(const ConvArgs& a);
+int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s);
+
 }  // namespace fnnu
