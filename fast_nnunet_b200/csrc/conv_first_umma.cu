@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kFirstThreads, 2) conv_first_umma_kernel(const
     int cur_b = -1;
     float sc = 1.f, sh = 0.f, sl = 1.f;
     // IDENT: the source has no pending transform (the network input).  Then a load has no dependent arithmetic and
-    // really is two row periods ahead; with the transform applied at load time every one of the 9 loads of a row
-    // exposed its latency (clock64: 3060 of 3500 cycles per row in load_row).
+    // really is one row period ahead of its first use; with the transform applied at load time every one of the 9
+    // loads of a row exposed its latency (clock64: 3060 of 3500 cycles per row in load_row).
     auto produce = [&](auto ident_tag) {
     constexpr bool IDENT = decltype(ident_tag)::value;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
