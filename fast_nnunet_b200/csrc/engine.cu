@@ -303,8 +303,10 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       a.w = wd;
       if (p.w_umma_bytes[i]) {
         void* wu = pa + p.w_umma_off[i];
-        a.use_rows = rows_supported(a) ? 1 : 0;
-        rc = a.use_rows ? launch_pack_weights_rows(staging, wu, a, s) : launch_pack_weights_umma(staging, wu, a, s);
+        a.use_rows = zrows_supported(a) ? 2 : (rows_supported(a) ? 1 : 0);
+        rc = a.use_rows == 2 ? launch_pack_weights_zrows(staging, wu, a, s)
+             : a.use_rows   ? launch_pack_weights_rows(staging, wu, a, s)
+                            : launch_pack_weights_umma(staging, wu, a, s);
         if (rc) { delete e; return rc; }
         a.w_umma = wu;
       }
@@ -418,7 +420,9 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
     if (op.kind == FNNU_OP_CONV || op.kind == FNNU_OP_TCONV) {
       op.conv.batch = batch;
       if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
-        rc = op.conv.use_rows ? launch_conv_rows(op.conv, s) : launch_conv_umma(op.conv, s);
+        rc = op.conv.use_rows == 2 ? launch_conv_zrows(op.conv, s)
+             : op.conv.use_rows   ? launch_conv_rows(op.conv, s)
+                                  : launch_conv_umma(op.conv, s);
         ++umma;
       } else if (e->backend == 0 && direct_specialised(op.conv)) {
         rc = launch_conv_specialised(op.conv, s);

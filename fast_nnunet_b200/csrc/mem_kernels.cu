@@ -11,6 +11,8 @@
 
 namespace fnnu {
 
+static int64_t g_mem_launches = 0;   // kernels launched by the memory-bound entry points (bench evidence)
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -232,6 +234,152 @@ __global__ void __launch_bounds__(256) accumulate_h2_vec4_kernel(
   }
 }
 
+// Cluster path (fp16 predictions, fp32 accumulators, z starts / extents multiples of VZ): ONE launch applies a group
+// of up to 8 tiles that overlap each other.  A thread owns VZ consecutive z voxels x HC heads of the group's bounding
+// box, loads the accumulator once, adds the contribution of every covering tile IN TILE ORDER (the reference's
+// summation order, bit for bit: acc = (acc + c_t0) + c_t1 ...) and stores once — overlapping tiles cost one
+// read-modify-write per voxel instead of one per tile, and no launch boundary is needed between them.
+// Heads are contiguous per voxel in the channels-last prediction: a voxel's HC heads are one 4 / 8 / 16 / 32-byte load.
+struct TileCluster {
+  int n;
+  int sx[FNNU_ROUND_MAX], sy[FNNU_ROUND_MAX], sz[FNNU_ROUND_MAX];
+  int idx[FNNU_ROUND_MAX];
+  int ox, oy, oz;       // bounding box origin (accumulator coordinates)
+  int bx, by, bz;       // bounding box extents
+};
+
+template <int HC>
+__device__ __forceinline__ void load_heads(const __half* p, float* out) {
+  if constexpr (HC == 2) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(p));
+    out[0] = v.x; out[1] = v.y;
+  } else if constexpr (HC == 4) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float2 v = __half22float2(h[k]);
+      out[2 * k] = v.x; out[2 * k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < HC / 8; ++q) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p) + q);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = __half22float2(h[k]);
+        out[8 * q + 2 * k] = v.x; out[8 * q + 2 * k + 1] = v.y;
+      }
+    }
+  }
+}
+
+template <int HC, int VZ>
+__global__ void __launch_bounds__(256) accumulate_cluster_kernel(
+    const __half* __restrict__ preds_all, int ps, int heads, TileCluster tc, int pX, int pY, int pZ, FlipList flips,
+    int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
+  const int zq = tc.bz / VZ;
+  const size_t total = (size_t)tc.bx * tc.by * zq;
+  const size_t pvox = (size_t)pX * pY * pZ;
+  const size_t hstride = (size_t)X * Y * Z;
+  const float nf = (float)n_flips;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int gz = tc.oz + (int)(i % zq) * VZ;
+    const int gy = tc.oy + (int)((i / zq) % tc.by);
+    const int gx = tc.ox + (int)(i / ((size_t)zq * tc.by));
+    float* const a0 = acc + ((size_t)gx * Y + gy) * Z + gz;
+    for (int h0 = 0; h0 < heads; h0 += HC) {
+      float r[VZ][HC];
+      bool any = false;
+      for (int t = 0; t < tc.n; ++t) {
+        const int lx = gx - tc.sx[t], ly = gy - tc.sy[t], lz = gz - tc.sz[t];
+        if ((unsigned)lx >= (unsigned)pX || (unsigned)ly >= (unsigned)pY || (unsigned)lz >= (unsigned)pZ) continue;
+        if (!any) {
+          any = true;
+#pragma unroll
+          for (int j = 0; j < HC; ++j) {
+            if (h0 + j < heads) {
+              if constexpr (VZ == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(a0 + (size_t)(h0 + j) * hstride);
+                r[0][j] = v.x; r[1][j] = v.y; r[2][j] = v.z; r[3][j] = v.w;
+              } else {
+                const float2 v = *reinterpret_cast<const float2*>(a0 + (size_t)(h0 + j) * hstride);
+                r[0][j] = v.x; r[1][j] = v.y;
+              }
+            }
+          }
+        }
+        const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pvox * ps + h0;
+        float s[VZ][HC];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          if (f < n_flips) {
+            const int m = flips.m[f];
+            const int fx = (m & 1) ? pX - 1 - lx : lx;
+            const int fy = (m & 2) ? pY - 1 - ly : ly;
+            const bool rz = (m & 4) != 0;
+            const int fz = rz ? pZ - VZ - lz : lz;
+            const __half* src = preds + ((size_t)f * pvox + ((size_t)fx * pY + fy) * pZ + fz) * ps;
+            if (HC * VZ <= 16 && ps == HC) {
+              // the thread's VZ voxels x HC heads are contiguous: one or two 128-bit loads
+              float blockv[VZ * HC];
+#pragma unroll
+              for (int q = 0; q < VZ * HC / 8; ++q) load_heads<8>(src + q * 8, blockv + q * 8);
+#pragma unroll
+              for (int v = 0; v < VZ; ++v)
+#pragma unroll
+                for (int j = 0; j < HC; ++j) {
+                  const float pv = rz ? blockv[(VZ - 1 - v) * HC + j] : blockv[v * HC + j];
+                  s[v][j] = (f == 0) ? pv : __fadd_rn(s[v][j], pv);
+                }
+            } else {
+#pragma unroll
+              for (int v = 0; v < VZ; ++v) {
+                float piece[HC];
+                load_heads<HC>(src + (size_t)(rz ? VZ - 1 - v : v) * ps, piece);
+#pragma unroll
+                for (int j = 0; j < HC; ++j) s[v][j] = (f == 0) ? piece[j] : __fadd_rn(s[v][j], piece[j]);
+              }
+            }
+          }
+        }
+        float g[VZ];
+#pragma unroll
+        for (int v = 0; v < VZ; ++v) g[v] = 1.f;
+        if (gauss) {
+          const __half* gp = gauss + ((size_t)lx * pY + ly) * pZ + lz;
+#pragma unroll
+          for (int v = 0; v < VZ; v += 2) {
+            const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gp + v));
+            g[v] = gv.x; g[v + 1] = gv.y;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < VZ; ++v)
+#pragma unroll
+          for (int j = 0; j < HC; ++j) {
+            float c = s[v][j];
+            if (n_flips > 1) c = __fdiv_rn(c, nf);
+            if (gauss) c = __fmul_rn(c, g[v]);
+            r[v][j] = __fadd_rn(r[v][j], c);
+          }
+      }
+      if (any) {
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          if (h0 + j < heads) {
+            if constexpr (VZ == 4)
+              *reinterpret_cast<float4*>(a0 + (size_t)(h0 + j) * hstride) = make_float4(r[0][j], r[1][j], r[2][j], r[3][j]);
+            else
+              *reinterpret_cast<float2*>(a0 + (size_t)(h0 + j) * hstride) = make_float2(r[0][j], r[1][j]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight sum (n_predictions): gather over the covering tiles, in tile order.
 // ------------------------------------------------------------------------------------------------
@@ -346,6 +494,45 @@ __global__ void __launch_bounds__(256) finalize_h2_vec4_kernel(const float* __re
   if (saw_inf && inf_flag) atomicOr(inf_flag, 1);
 }
 
+// Any number of heads, fp32 accumulators, nvox % 4 == 0: a thread normalises 4 consecutive voxels of every head
+// (128-bit loads, 64-bit logit stores, one 32-bit label store).
+__global__ void __launch_bounds__(256) finalize_vec4_kernel(const float* __restrict__ acc, const float* __restrict__ wsum,
+                                                            int heads, size_t nvox, size_t hs, __half* __restrict__ logits,
+                                                            uint8_t* __restrict__ labels, int32_t* __restrict__ inf_flag) {
+  bool saw_inf = false;
+  const size_t nq = nvox >> 2;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wsum) + q);
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+    float best[4];
+    uint32_t arg[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int h = 0; h < heads; ++h) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(acc + (size_t)h * hs) + q);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      __half hv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hv[k] = __float2half_rn(__fdiv_rn(av[k], wv[k]));
+        const float r = __half2float(hv[k]);
+        if (isinf(r)) saw_inf = true;
+        if (h == 0 || r > best[k]) {      // strict '>' keeps the first maximum (numpy argmax)
+          best[k] = r;
+          arg[k] = (uint32_t)h;
+        }
+      }
+      if (logits) {
+        uint2 o;
+        o.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
+        o.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
+        reinterpret_cast<uint2*>(logits + (size_t)h * nvox)[q] = o;
+      }
+    }
+    if (labels) reinterpret_cast<uint32_t*>(labels)[q] = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  }
+  if (saw_inf && inf_flag) atomicOr(inf_flag, 1);
+}
+
 __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ acc,
                                                           const float* __restrict__ other, size_t n, int aligned) {
   const size_t nq = aligned ? (n >> 2) : 0;
@@ -390,12 +577,14 @@ extern "C" int fnnu_gather_tiles(const float* volume, int channels, const int vo
         volume, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1], patch[2], fl, n_flips,
         (__half*)out);
     FNNU_LAUNCH_CHECK();
+    ++g_mem_launches;
     return FNNU_OK;
   }
   gather_tiles_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       volume, channels, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1],
       patch[2], fl, n_flips, (__half*)out, c_stride);
   FNNU_LAUNCH_CHECK();
+  ++g_mem_launches;
   return FNNU_OK;
 }
 
@@ -423,15 +612,73 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
                    "accumulate: tile %d (%d,%d,%d) outside the volume", t, sx, sy, sz);
     if (sz % 4 != 0) vec = false;
   }
-  // rounds: round[t] = 1 + max round of the earlier tiles that overlap t (0 if none)
+  auto overlaps = [&](int t, int u) {
+    return abs(starts_host[t * 3] - starts_host[u * 3]) < pX && abs(starts_host[t * 3 + 1] - starts_host[u * 3 + 1]) < pY &&
+           abs(starts_host[t * 3 + 2] - starts_host[u * 3 + 2]) < pZ;
+  };
+  // ---- cluster path: groups of <= 8 consecutive tiles, one launch per group over its bounding box ----
+  int hc = 0, vz = 4;
+  if (in_dtype == FNNU_IN_F16 && acc_dtype == FNNU_ACC_F32 && ((uintptr_t)preds % 16 == 0) && ((uintptr_t)acc % 16 == 0) &&
+      (!gaussian || ((uintptr_t)gaussian) % 4 == 0)) {
+    if (p_stride == 2 && heads == 2) hc = 2;
+    else if (p_stride == 4) hc = 4;
+    else if (p_stride == 8) hc = 8;
+    else if (p_stride % 16 == 0) { hc = 16; vz = 2; }
+    else if (p_stride % 8 == 0) hc = 8;
+    if (hc && (pZ % vz || Z % vz)) hc = 0;
+    for (int t = 0; t < n_tiles && hc; ++t)
+      if (starts_host[t * 3 + 2] % vz) hc = 0;
+    static int cluster_enabled = -1;
+    if (cluster_enabled < 0) {
+      const char* e = getenv("FNNU_ACC_CLUSTER");
+      cluster_enabled = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!cluster_enabled) hc = 0;
+  }
+  if (hc) {
+    int t = 0;
+    while (t < n_tiles) {
+      // a group: consecutive tiles, each overlapping at least one earlier tile of the group (so that the bounding box
+      // stays tight); non-overlapping neighbours start a new group
+      TileCluster tc;
+      tc.n = 0;
+      int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      for (; t < n_tiles && tc.n < FNNU_ROUND_MAX; ++t) {
+        bool joins = tc.n == 0;
+        for (int k = 0; k < tc.n && !joins; ++k) joins = overlaps(t, tc.idx[k]);
+        if (!joins) break;
+        const int st[3] = {starts_host[t * 3], starts_host[t * 3 + 1], starts_host[t * 3 + 2]};
+        const int pp[3] = {pX, pY, pZ};
+        for (int a = 0; a < 3; ++a) {
+          if (tc.n == 0 || st[a] < lo[a]) lo[a] = st[a];
+          if (tc.n == 0 || st[a] + pp[a] > hi[a]) hi[a] = st[a] + pp[a];
+        }
+        tc.sx[tc.n] = st[0]; tc.sy[tc.n] = st[1]; tc.sz[tc.n] = st[2];
+        tc.idx[tc.n] = t;
+        ++tc.n;
+      }
+      tc.ox = lo[0]; tc.oy = lo[1]; tc.oz = lo[2];
+      tc.bx = hi[0] - lo[0]; tc.by = hi[1] - lo[1]; tc.bz = hi[2] - lo[2];
+      const size_t items = (size_t)tc.bx * tc.by * (tc.bz / vz);
+      const int grid = grid_for(items, 256, 32);
+      const __half* pr = (const __half*)preds;
+      const __half* gs = (const __half*)gaussian;
+      float* ac = (float*)acc;
+      if (hc == 2) accumulate_cluster_kernel<2, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
+      else if (hc == 4) accumulate_cluster_kernel<4, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
+      else if (hc == 8) accumulate_cluster_kernel<8, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
+      else accumulate_cluster_kernel<16, 2><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
+      FNNU_LAUNCH_CHECK();
+      ++g_mem_launches;
+    }
+    return FNNU_OK;
+  }
+  // ---- round path (any dtype / alignment): round[t] = 1 + max round of the earlier tiles that overlap t ----
   std::vector<int> round(n_tiles, 0);
   int n_rounds = 0;
   for (int t = 0; t < n_tiles; ++t) {
-    for (int u = 0; u < t; ++u) {
-      bool ov = abs(starts_host[t * 3] - starts_host[u * 3]) < pX && abs(starts_host[t * 3 + 1] - starts_host[u * 3 + 1]) < pY &&
-                abs(starts_host[t * 3 + 2] - starts_host[u * 3 + 2]) < pZ;
-      if (ov && round[u] + 1 > round[t]) round[t] = round[u] + 1;
-    }
+    for (int u = 0; u < t; ++u)
+      if (overlaps(t, u) && round[u] + 1 > round[t]) round[t] = round[u] + 1;
     if (round[t] + 1 > n_rounds) n_rounds = round[t] + 1;
   }
   for (int r = 0; r < n_rounds; ++r) {
@@ -468,10 +715,13 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
                                                                         n_flips, (const __half*)gaussian, (__half*)acc, X, Y, Z);
       }
       FNNU_LAUNCH_CHECK();
+      ++g_mem_launches;
     }
   }
   return FNNU_OK;
 }
+
+extern "C" long long fnnu_mem_launches(void) { return (long long)g_mem_launches; }
 
 extern "C" int fnnu_weight_sum(const int32_t* steps_x, int nx, const int32_t* steps_y, int ny,
                                const int32_t* steps_z, int nz, const int patch[3], const void* gaussian,
@@ -513,6 +763,10 @@ extern "C" int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, i
   if (vec)
     finalize_h2_vec4_kernel<<<grid_for(nvox / 4, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, nvox, hs,
                                                                     (__half*)logits_out, labels_out, inf_flag_dev);
+  else if (acc_dtype == FNNU_ACC_F32 && nvox % 4 == 0 && hs % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)wsum % 16 == 0) &&
+           (!logits_out || (uintptr_t)logits_out % 8 == 0) && (!labels_out || (uintptr_t)labels_out % 4 == 0))
+    finalize_vec4_kernel<<<grid_for(nvox / 4, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, heads, nvox, hs,
+                                                                 (__half*)logits_out, labels_out, inf_flag_dev);
   else if (acc_dtype == FNNU_ACC_F32)
     finalize_kernel<float><<<grid_for(nvox, 256), 256, 0, s>>>((const float*)acc, (const float*)wsum, heads, nvox, hs,
                                                                (__half*)logits_out, labels_out, inf_flag_dev);

@@ -17,7 +17,7 @@ struct ConvArgs {
   int dst_stat_stride;
   const float* w;           // direct kernel: [tap][cin][cout_pad] fp32
   const void* w_umma;       // tcgen05 kernels: packed fp16 blob (conv_umma.cu / conv_umma_rows.cu) or nullptr
-  int use_rows;             // w_umma is packed for the row-streaming kernel
+  int use_rows;             // w_umma is packed for a row-streaming kernel: 1 = conv_umma_rows.cu, 2 = conv_umma_zrows.cu
   const float* bias;        // [cout] or nullptr
   int cin, cout, cout_pad;
   int in_d[3], out_d[3];
@@ -71,7 +71,13 @@ bool rows_supported(const ConvArgs& a);
 int launch_pack_weights_rows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_rows(const ConvArgs& a, cudaStream_t s);
 
-// conv_first_umma.cu: Cin == 1 first layer with the taps as the K dimension of the MMA (FNNU_FIRST_LAYER_TC=1)
+// z-pair row-streaming kernel (conv_umma_zrows.cu): Cout <= 16, Cin 16 | 32, 3x3x3, even depth; FNNU_ZROWS=0 disables it
+bool zrows_supported(const ConvArgs& a);
+int launch_pack_weights_zrows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
+int launch_conv_zrows(const ConvArgs& a, cudaStream_t s);
+
+// conv_first_umma.cu: Cin == 1 first layer with the taps as the K dimension of the MMA (on by default;
+// FNNU_FIRST_LAYER_TC=0 restores the CUDA-core kernel)
 bool first_umma_supported(const ConvArgs& a);
 int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s);
 

@@ -87,6 +87,10 @@ int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, int heads, c
                   size_t acc_head_stride, void* logits_out, uint8_t* labels_out, int32_t* inf_flag_dev,
                   void* stream);
 
+/* Number of kernels the memory-bound entry points above have launched in this process (bench.py's
+ * gpu_launches evidence; fnnu_engine_launch_counts gives the network's). */
+long long fnnu_mem_launches(void);
+
 /* Multi-GPU halo step: acc += other over a contiguous range of n elements (fp32). */
 int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream);
 

@@ -8,7 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _exact_fp32_oracle():
+    """The oracle is the reference's fp32 arithmetic: no TF32 (10-bit mantissa) in cuDNN / cuBLAS when it runs on
+    the GPU box, otherwise the "fp32 oracle" would be no more precise than the fp16 engine it checks."""
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _exact_fp32_oracle()
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
