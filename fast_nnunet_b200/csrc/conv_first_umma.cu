@@ -313,18 +313,10 @@ int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s) {
   if (smem < 78 * 1024) smem = 78 * 1024;
   int grid = p.n_units < 2 * num_sms() ? p.n_units : 2 * num_sms();
   if (a.k[0] == 3) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      FNNU_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr_set = true;
-    }
+    /* the attribute is per device: set it on every launch (cheap) */ FNNU_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     conv_first_umma_kernel<3><<<grid, kFirstThreads, smem, s>>>(p);
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      FNNU_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr_set = true;
-    }
+    /* the attribute is per device: set it on every launch (cheap) */ FNNU_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     conv_first_umma_kernel<1><<<grid, kFirstThreads, smem, s>>>(p);
   }
   FNNU_LAUNCH_CHECK();

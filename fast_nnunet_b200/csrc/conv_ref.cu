@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(256) conv_pointwise_head_kernel(ConvArgs a) {
   float bias[COUT];
 #pragma unroll
   for (int o = 0; o < COUT; ++o) bias[o] = (a.bias && o < a.cout) ? __ldg(a.bias + o) : 0.f;
+  const bool vec_out = a.dst_cs >= COUT && (a.dst_cs * 2) % (COUT * 2) == 0 && ((uintptr_t)a.dst % (COUT * 2)) == 0;
   for (size_t v = (size_t)blockIdx.x * 256 + threadIdx.x; v < nv; v += (size_t)gridDim.x * 256) {
     float acc[COUT];
 #pragma unroll
@@ -449,9 +450,19 @@ __global__ void __launch_bounds__(256) conv_pointwise_head_kernel(ConvArgs a) {
       }
     }
     __half* q = dst_b + v * a.dst_cs;
+    if (vec_out) {
+      // the destination holds COUT (padded) heads per voxel: one 4 / 8 / 16-byte store (padding heads are zeros)
+      __half2 h[COUT / 2];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o)
-      if (o < a.cout) q[o] = __float2half_rn(acc[o]);
+      for (int o = 0; o < COUT; o += 2) h[o >> 1] = __floats2half2_rn(acc[o], acc[o + 1]);
+      if constexpr (COUT == 2) *reinterpret_cast<__half2*>(q) = h[0];
+      else if constexpr (COUT == 4) *reinterpret_cast<uint2*>(q) = *reinterpret_cast<uint2*>(h);
+      else *reinterpret_cast<uint4*>(q) = *reinterpret_cast<uint4*>(h);
+    } else {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o)
+        if (o < a.cout) q[o] = __float2half_rn(acc[o]);
+    }
   }
 }
 

@@ -641,11 +641,7 @@ int launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     return FNNU_E_UNSUPPORTED;
   }
   p.n_units = a.batch * p.c.n_chunks * p.c.n_yblocks * p.c.Dz;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
-  }
+  /* the attribute is per device: set it on every launch (cheap) */ FNNU_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   int grid = p.n_units < num_sms() ? p.n_units : num_sms();
   static const bool show_plan = getenv("FNNU_SHOW_PLAN") != nullptr;   // debugging aid: one line per launch
   if (show_plan) {

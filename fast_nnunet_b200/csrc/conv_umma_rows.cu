@@ -532,12 +532,8 @@ int launch_conv_rows(const ConvArgs& a, cudaStream_t s) {
   int grid = p.n_units < num_sms() * p.c.occ ? p.n_units : num_sms() * p.c.occ;
 #define FNNU_ROWS_CASE(CPV, CHV, OCCV)                                                                                    \
   if (a.cout_pad == CPV && p.c.chunks == CHV && p.c.occ == OCCV) {                                                                 \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<CPV, CHV, OCCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     kRowsSmemLimit));                                                               \
-      attr_set = true;                                                                                               \
-    }                                                                                                                \
+    /* the attribute is per device: set it on every launch (cheap) */ FNNU_CUDA(cudaFuncSetAttribute(conv_umma_rows_kernel<CPV, CHV, OCCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     kRowsSmemLimit));                                                                                                                \
     conv_umma_rows_kernel<CPV, CHV, OCCV><<<grid, kRowsThreads, p.c.smem_bytes, s>>>(p);                                   \
   }
   FNNU_ROWS_CASE(16, 1, 1)

@@ -59,7 +59,7 @@ namespace {
 struct Plan {
   size_t param_bytes = 0, workspace_bytes = 0;
   std::vector<size_t> buf_off, stat_off, meta_off;
-  std::vector<size_t> w_direct_off, w_umma_off, bias_off;
+  std::vector<size_t> w_direct_off, w_umma_off, bias_off, staging_op_off;
   std::vector<size_t> w_umma_bytes;
   size_t staging_off = 0, staging_bytes = 0;
   size_t stats_off = 0, stats_bytes = 0;
@@ -146,6 +146,7 @@ void make_plan(const fnnu_buffer_desc* bufs, int n_bufs, const fnnu_op_desc* ops
   p.w_umma_off.assign(n_ops, 0);
   p.w_umma_bytes.assign(n_ops, 0);
   p.bias_off.assign(n_ops, 0);
+  p.staging_op_off.assign(n_ops, 0);
   size_t stage = 0;
   for (int i = 0; i < n_ops; ++i) {
     const fnnu_op_desc& o = ops[i];
@@ -162,8 +163,10 @@ void make_plan(const fnnu_buffer_desc* bufs, int n_bufs, const fnnu_op_desc* ops
     }
     p.bias_off[i] = q;
     q += align_up((size_t)o.cout * sizeof(float), 256);
-    size_t raw = (size_t)nt * o.cin * o.cout * sizeof(float);
-    if (raw > stage) stage = raw;
+    // every op has its own slice of the staging area: the raw fp32 weights of all ops are uploaded back to back and
+    // packed on the stream without a host synchronisation per op (a 5-fold ensemble creates 5 engines per model)
+    p.staging_op_off[i] = stage;
+    stage += align_up((size_t)nt * o.cin * o.cout * sizeof(float), 256);
   }
   p.staging_off = q;
   p.staging_bytes = align_up(stage, 256);
@@ -245,8 +248,8 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
         metas[o.dst][o.dst_coff + c] = ChanMeta{o.gamma[c], o.beta[c], o.act_slope, o.norm_eps};
   }
   for (int i = 0; i < n_bufs; ++i) {
+    // pageable source: cudaMemcpyAsync returns once the bytes sit in the driver's staging buffer
     cudaError_t ce = cudaMemcpyAsync(e->bufs[i].meta, metas[i].data(), metas[i].size() * sizeof(ChanMeta), cudaMemcpyHostToDevice, s);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) {
       set_error("engine_create: meta upload failed: %s", cudaGetErrorString(ce));
       delete e;
@@ -288,10 +291,9 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
         a.pad[ax] = a.transposed ? 0 : (o.kernel[ax] - 1) / 2;
       }
       // upload + pack weights
-      float* staging = (float*)(pa + p.staging_off);
+      float* staging = (float*)(pa + p.staging_off + p.staging_op_off[i]);
       size_t raw = (size_t)a.ntaps * o.cin * o.cout * sizeof(float);
       cudaError_t ce = cudaMemcpyAsync(staging, o.weight, raw, cudaMemcpyHostToDevice, s);
-      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
       if (ce != cudaSuccess) {
         set_error("engine_create: weight upload of op %d failed: %s", i, cudaGetErrorString(ce));
         delete e;
@@ -317,7 +319,6 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       } else {
         a.bias = nullptr;
       }
-      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);   // staging is reused by the next op
       if (ce != cudaSuccess) {
         set_error("engine_create: op %d parameter upload failed: %s", i, cudaGetErrorString(ce));
         delete e;
@@ -351,6 +352,14 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       a.inv_count = 1.0 / (double)sb.nvox;
       a.slope = o.act_slope;
       a.batch = 1;
+    }
+  }
+  {
+    cudaError_t ce = cudaStreamSynchronize(s);   // ONE synchronisation: the caller's host arrays may go away now
+    if (ce != cudaSuccess) {
+      set_error("engine_create: parameter upload failed: %s", cudaGetErrorString(ce));
+      delete e;
+      return FNNU_E_CUDA;
     }
   }
   *out = e;

@@ -548,6 +548,11 @@ __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ ac
     acc[i] += other[i];
 }
 
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ x, float f, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = __fmul_rn(x[i], f);
+}
+
 static inline int grid_for(size_t work_items, int threads, int waves_cap = 16) {
   size_t blocks = (work_items + threads - 1) / threads;
   size_t cap = (size_t)num_sms() * waves_cap;
@@ -774,6 +779,15 @@ extern "C" int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, i
     finalize_kernel<__half><<<grid_for(nvox, 256), 256, 0, s>>>((const __half*)acc, (const __half*)wsum, heads, nvox, hs,
                                                                 (__half*)logits_out, labels_out, inf_flag_dev);
   FNNU_LAUNCH_CHECK();
+  return FNNU_OK;
+}
+
+extern "C" int fnnu_scale_inplace_f32(float* x, float factor, size_t n, void* stream) {
+  FNNU_CHECK_ARG(x, "scale_inplace: null pointer");
+  if (n == 0) return FNNU_OK;
+  scale_inplace_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, factor, n);
+  FNNU_LAUNCH_CHECK();
+  ++g_mem_launches;
   return FNNU_OK;
 }
 

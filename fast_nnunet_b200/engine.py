@@ -32,7 +32,9 @@ def require_cuda_device(device: torch.device):
 class NetworkEngine:
     """A compiled network program for up to `max_batch` patches per launch sequence."""
 
-    def __init__(self, program: Program, max_batch: int, device: torch.device):
+    def __init__(self, program: Program, max_batch: int, device: torch.device, share_workspace_with=None):
+        """`share_workspace_with`: another engine of the SAME program shape (another fold): the activation workspace
+        is shared, only the packed parameters are separate."""
         self.lib = _lib.load()
         require_cuda_device(device)
         self.program = program
@@ -65,7 +67,11 @@ class NetworkEngine:
         self.param_bytes, self.workspace_bytes = pb.value, wb.value
         with torch.cuda.device(device):
             self.param_arena = torch.empty(self.param_bytes + 256, dtype=torch.uint8, device=device)
-            self.workspace = torch.zeros(self.workspace_bytes + 256, dtype=torch.uint8, device=device)
+            if share_workspace_with is not None:
+                assert share_workspace_with.workspace_bytes == self.workspace_bytes
+                self.workspace = share_workspace_with.workspace
+            else:
+                self.workspace = torch.zeros(self.workspace_bytes + 256, dtype=torch.uint8, device=device)
             self._pa = (self.param_arena.data_ptr() + 255) // 256 * 256
             self._ws = (self.workspace.data_ptr() + 255) // 256 * 256
             h = C.c_void_p(0)
@@ -167,6 +173,16 @@ def finalize(acc: torch.Tensor, wsum: torch.Tensor, logits_out: Optional[torch.T
     _lib.check(lib.fnnu_finalize(_ptr(acc), _ptr(wsum), acc_dtype, acc.shape[0], _lib.i3(acc.shape[1:]),
                                  head_stride, _ptr(logits_out), _ptr(labels_out), _ptr(inf_flag),
                                  _lib.stream_ptr()))
+
+
+def scale_inplace(x: torch.Tensor, factor: float):
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _lib.check(lib.fnnu_scale_inplace_f32(_ptr(x), C.c_float(factor), x.numel(), _lib.stream_ptr()))
+
+
+def mem_launches() -> int:
+    return int(_lib.load().fnnu_mem_launches())
 
 
 def add_inplace(acc: torch.Tensor, other: torch.Tensor):

@@ -63,9 +63,10 @@ def student_blocks(n_blocks, features, lite_features, strategy):
 
 
 def effective_arch(network_class_name: str, arch_kwargs: dict, trainer_name: str, init_args: dict,
-                   plans_name: str = '') -> (str, dict):
+                   plans_name: str = '', state_dict: Optional[dict] = None) -> (str, dict):
     """Architecture actually stored in the checkpoint: the plans' arch_kwargs for a teacher; the reduced
-    one for a distilled student."""
+    one for a distilled student.  Plain vs residual encoder is read off the checkpoint's own keys when a
+    state_dict is given (a LiteNNUNetStudent distilled from a ResEnc teacher keeps the teacher's plans)."""
     kw = deepcopy(arch_kwargs)
     cls = network_class_name
     if trainer_name in STUDENT_TRAINERS:
@@ -73,10 +74,14 @@ def effective_arch(network_class_name: str, arch_kwargs: dict, trainer_name: str
         feats = [int(f) for f in kw['features_per_stage']]
         lite = student_features(feats, r)
         kw['features_per_stage'] = lite
-        is_resenc = 'ResEnc' in (init_args.get('student_plans_identifier') or plans_name or '') or \
-                    cls.endswith('ResidualEncoderUNet')
+        if state_dict is not None:
+            from .program import clean_state_dict
+            is_resenc = 'encoder.stem.convs.0.conv.weight' in clean_state_dict(state_dict)
+        else:
+            # the reference's rule (nnUNetDistillationTrainer.py:615)
+            is_resenc = 'ResEnc' in (init_args.get('student_plans_identifier') or plans_name or '')
         if is_resenc:
-            nb = kw.get('n_blocks_per_stage', [1, 3, 4, 6, 6, 6][:kw['n_stages']])
+            nb = kw.get('n_blocks_per_stage') or [1, 3, 4, 6, 6, 6][:kw['n_stages']]
             kw['n_blocks_per_stage'] = student_blocks(list(nb), feats, lite,
                                                       init_args.get('block_reduction_strategy', 'keep'))
             kw.pop('n_conv_per_stage', None)

@@ -58,8 +58,12 @@ def _infer_arch_from_weights(cls_name: str, kw: dict, sd: dict) -> dict:
 
 
 class CompiledNetwork:
-    """Stands where the reference keeps `self.network` (an nn.Module).  `load_state_dict` lowers the
-    weights into a libfnnu engine; calling it runs a batch of channels-first patches (tests)."""
+    """Stands where the reference keeps `self.network` (an nn.Module).  `load_state_dict` selects a set of
+    weights; the first use lowers it into a libfnnu engine, which then stays resident (one per fold, sharing one
+    activation workspace), so that a multi-fold ensemble never re-packs or re-uploads parameters
+    (predict_from_raw_data.py:483-500 re-loads the state_dict per fold per case)."""
+
+    MAX_RESIDENT = 8        # parameter sets kept lowered at the same time (5 folds + head-room)
 
     def __init__(self, network_class_name: str, arch_kwargs: dict, in_channels: int, num_heads: int,
                  patch_size: Sequence[int]):
@@ -69,8 +73,9 @@ class CompiledNetwork:
         self.num_heads = num_heads
         self.patch_size = tuple(int(p) for p in patch_size)
         self.device = None
-        self.max_batch = None
-        self._engines = {}
+        # every entry holds a strong reference to its state_dict, so the identity test below can never be
+        # fooled by a recycled id()
+        self._entries = []          # [{'params': dict, 'engines': {device str: NetworkEngine}}], most recent last
         self._current = None
         self.program: Optional[Program] = None
 
@@ -82,33 +87,55 @@ class CompiledNetwork:
     def eval(self):
         return self
 
+    def _entry_for(self, params: dict) -> dict:
+        for i, e in enumerate(self._entries):
+            if e['params'] is params:
+                self._entries.append(self._entries.pop(i))
+                return e
+        e = {'params': params, 'engines': {}}
+        self._entries.append(e)
+        while len(self._entries) > self.MAX_RESIDENT:
+            self._entries.pop(0)
+        return e
+
     def load_state_dict(self, params: dict, strict: bool = True):
-        self._current = params
+        self._current = self._entry_for(params)
         return self
 
-    def engine(self, device: torch.device, max_batch: int) -> E.NetworkEngine:
-        if self._current is None:
+    def engine(self, device: torch.device, max_batch: int, params: Optional[dict] = None) -> E.NetworkEngine:
+        """Engine of `params` (default: the set selected by load_state_dict) able to run `max_batch` patches."""
+        entry = self._current if params is None else self._entry_for(params)
+        if entry is None:
             raise RuntimeError('no parameters loaded (call load_state_dict / initialize_* first)')
-        key = (id(self._current), str(device), int(max_batch))
-        if key not in self._engines:
-            kw = _infer_arch_from_weights(self.network_class_name, self.arch_kwargs, self._current)
-            prog = build_program(self.network_class_name, self._current, kw, self.in_channels, self.num_heads,
+        key = str(device)
+        eng = entry['engines'].get(key)
+        if eng is None or eng.max_batch < int(max_batch):
+            kw = _infer_arch_from_weights(self.network_class_name, self.arch_kwargs, entry['params'])
+            prog = build_program(self.network_class_name, entry['params'], kw, self.in_channels, self.num_heads,
                                  self.patch_size)
-            self._engines = {k: v for k, v in self._engines.items() if k[0] == key[0]}   # one fold resident
-            self._engines[key] = E.NetworkEngine(prog, max_batch, device)
-            self.program = prog
-        return self._engines[key]
+            entry['engines'].pop(key, None)
+            share = None
+            for other in self._entries:
+                o = other['engines'].get(key)
+                if o is not None and o.max_batch == int(max_batch):
+                    share = o
+                    break
+            eng = E.NetworkEngine(prog, int(max_batch), device, share_workspace_with=share)
+            entry['engines'][key] = eng
+        self.program = eng.program
+        return eng
 
     @torch.inference_mode()
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        """x: (n, c, *patch) on the CUDA device -> logits (n, heads, *patch) fp16."""
+        """x: (n, c, *patch) on the CUDA device -> logits (n, heads, *patch) fp16.  What reference-side callers such
+        as nnUNetDistillationTrainer.load_teacher_model's `teacher_model(x.float())` (:781-789) get."""
         assert x.ndim == 5 and tuple(x.shape[2:]) == self.patch_size and x.shape[1] == self.in_channels
         eng = self.engine(x.device, max(int(x.shape[0]), 1))
         n = x.shape[0]
         inp = eng.buffer_tensor(eng.program.input_buffer, n)
         inp.copy_(x.permute(0, 2, 3, 4, 1))
         eng.forward(n)
-        out = eng.buffer_tensor(eng.program.output_buffer, n)
+        out = eng.buffer_tensor(eng.program.output_buffer, n)[..., :self.num_heads]
         return out.permute(0, 4, 1, 2, 3).contiguous()
 
 
@@ -149,6 +176,8 @@ class nnUNetPredictor(object):
         self.collect_timing = False     # bench: CUDA events around each phase of the tile loop
         self.timing = {}
         self._gauss_cache = {}
+        self._wsum_cache = {}           # n_predictions maps: input independent, 4 bytes per voxel -> keep the last two
+        self._pinned_cache = {}
 
     # ------------------------------------------------------------------ model loading
     def initialize_from_trained_model_folder(self, model_training_output_dir: str,
@@ -184,7 +213,7 @@ class nnUNetPredictor(object):
         label_manager = plans_manager.get_label_manager(dataset_json)
         cls, kw = effective_arch(configuration_manager.network_arch_class_name,
                                  configuration_manager.network_arch_init_kwargs, trainer_name, init_args,
-                                 plans_manager.plans.get('plans_name', ''))
+                                 plans_manager.plans.get('plans_name', ''), parameters[0])
         network = CompiledNetwork(cls, kw, num_input_channels, label_manager.num_segmentation_heads,
                                   configuration_manager.patch_size)
 
@@ -279,54 +308,99 @@ class nnUNetPredictor(object):
         # for 148 SMs; activations for 32 x 128^3 student patches take 15 GB of the 180 GB
         return max(1, min(n_tiles, max(1, 32 // n_flips)))
 
+    def _engine_capacity(self, n_flips: int) -> int:
+        """Patches per launch sequence the engines are built for — independent of the volume at hand, so that a
+        small volume (or a short shard) never builds a second engine + workspace."""
+        tpb = int(self.tiles_per_batch) if self.tiles_per_batch is not None else max(1, 32 // n_flips)
+        return max(1, tpb) * n_flips
+
+    @staticmethod
+    def _batch_sizes(n_tiles: int, tpb: int):
+        """Even split into ceil(n / tpb) batches: 37 tiles -> 4,4,4,4,4,4,4,3,3,3 instead of 9 x 4 + 1 (a 1-tile
+        batch runs the 8^3 / 4^3 layers on a handful of SMs)."""
+        nb = -(-n_tiles // tpb)
+        base, rem = divmod(n_tiles, nb)
+        return [base + 1] * rem + [base] * (nb - rem)
+
+    def _weight_sum(self, vol, patch, x_offset: int = 0, n_planes: Optional[int] = None, scale: float = 1.0,
+                    dtype=torch.float32) -> torch.Tensor:
+        """n_predictions (:590, :614) for planes [x_offset, x_offset + n_planes) of a volume, times `scale` (fold
+        count).  It does not depend on the image: computed once per geometry and kept."""
+        n_planes = vol[0] if n_planes is None else n_planes
+        key = (tuple(vol), tuple(patch), float(self.tile_step_size), bool(self.use_gaussian), str(dtype),
+               str(self.device), int(x_offset), int(n_planes), float(scale))
+        w = self._wsum_cache.get(key)
+        if w is None:
+            w = torch.empty((n_planes, vol[1], vol[2]), dtype=dtype, device=self.device)
+            steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
+            steps = [[s_ - x_offset for s_ in steps[0]], steps[1], steps[2]]
+            E.weight_sum(steps, patch, self._gaussian(patch), w)
+            if scale != 1.0:
+                assert dtype == torch.float32
+                E.scale_inplace(w, scale)
+            while len(self._wsum_cache) >= 2:
+                self._wsum_cache.pop(next(iter(self._wsum_cache)))
+            self._wsum_cache[key] = w
+        return w
+
+    def to_host(self, t: torch.Tensor) -> torch.Tensor:
+        """Device -> pinned host copy through a buffer that is reused across volumes (a pageable `.cpu()` of a
+        105 MB label map costs as much as the whole 8-GPU prediction)."""
+        key = (tuple(t.shape), t.dtype)
+        buf = self._pinned_cache.get(key)
+        if buf is None:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned_cache = {key: buf}
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return buf
+
     # ------------------------------------------------------------------ the hot path
     @torch.inference_mode()
     def _sliding_window_accumulate(self, data: torch.Tensor, starts: np.ndarray, acc: torch.Tensor,
-                                   acc_origin=(0, 0, 0)):
-        """Runs every tile in `starts` (volume coordinates) and adds its weighted prediction into `acc`,
-        whose voxel (0,0,0) sits at volume coordinate `acc_origin`."""
+                                   acc_origin=(0, 0, 0), data_origin=(0, 0, 0), all_folds: bool = False):
+        """Runs every tile in `starts` (volume coordinates) and adds its weighted prediction into `acc`, whose
+        voxel (0,0,0) sits at volume coordinate `acc_origin`; `data` voxel (0,0,0) sits at `data_origin`.
+        With `all_folds` every parameter set of list_of_parameters runs on the SAME gathered batch and is summed
+        into the same accumulator (the caller divides by the fold count through the weight sum)."""
         patch = tuple(self.configuration_manager.patch_size)
         flips = self._flip_masks()
         nf = len(flips)
         tpb = self._choose_tiles_per_batch(nf, len(starts))
-        eng = self.network.engine(self.device, tpb * nf)
-        prog = eng.program
+        cap = max(self._engine_capacity(nf), tpb * nf)
+        if all_folds and self.list_of_parameters:
+            engines = [self.network.engine(self.device, cap, params) for params in self.list_of_parameters]
+        else:
+            engines = [self.network.engine(self.device, cap)]
+        prog = engines[0].program
         heads = self.label_manager.num_segmentation_heads
         assert prog.num_heads == heads
         gauss = self._gaussian(patch)
         starts = np.ascontiguousarray(starts, dtype=np.int32)
-        starts_dev = torch.from_numpy(starts).to(self.device)
         local = starts - np.asarray(acc_origin, dtype=np.int32)[None]
-        in_ptr = eng.buffer_ptr(prog.input_buffer)
-        out_ptr = eng.buffer_ptr(prog.output_buffer)
+        in_vol = np.ascontiguousarray(starts - np.asarray(data_origin, dtype=np.int32)[None])
+        starts_dev = torch.from_numpy(in_vol).to(self.device)
         in_cs = prog.buffers[prog.input_buffer][1]
         out_cs = prog.buffers[prog.output_buffer][1]
         launches = 0
+        m0 = E.mem_launches()
         self.last_tiles_per_batch = tpb
-        for i in range(0, len(starts), tpb):
-            n = min(tpb, len(starts) - i)
+        i = 0
+        for n in self._batch_sizes(len(starts), tpb):
             self._mark('gather')
-            E.gather_tiles(data, starts_dev[i:i + n], n, patch, flips, in_ptr, in_cs)
-            self._mark('forward')
-            eng.forward(n * nf)
-            self._mark('accumulate')
-            E.accumulate_tiles(out_ptr, _lib.IN_F16, out_cs, heads, local[i:i + n], patch, flips, gauss, acc)
+            # folds share the workspace: ONE gather feeds every fold's forward
+            E.gather_tiles(data, starts_dev[i:i + n], n, patch, flips, engines[0].buffer_ptr(prog.input_buffer), in_cs)
+            for eng in engines:
+                assert eng.buffer_ptr(prog.input_buffer) == engines[0].buffer_ptr(prog.input_buffer)
+                self._mark('forward')
+                eng.forward(n * nf)
+                self._mark('accumulate')
+                E.accumulate_tiles(eng.buffer_ptr(prog.output_buffer), _lib.IN_F16, out_cs, heads, local[i:i + n], patch,
+                                   flips, gauss, acc)
+                launches += eng.launch_counts()[0]
             self._mark(None)
-            launches += 1 + eng.launch_counts()[0] + self._accumulate_rounds(local[i:i + n], patch)
-        self.last_launches += launches
-
-    @staticmethod
-    def _accumulate_rounds(starts, patch) -> int:
-        """Number of kernels fnnu_accumulate_tiles launches for these tiles: tiles are applied in rounds of mutually
-        non-overlapping tiles (round = 1 + max round of the earlier overlapping tiles), at most 8 tiles per launch."""
-        rounds = []
-        for t, s in enumerate(starts):
-            r = 0
-            for u in range(t):
-                if all(abs(int(s[a]) - int(starts[u][a])) < patch[a] for a in range(3)):
-                    r = max(r, rounds[u] + 1)
-            rounds.append(r)
-        return sum((rounds.count(r) + 7) // 8 for r in set(rounds))
+            i += n
+        self.last_launches += launches + (E.mem_launches() - m0)
 
     @torch.inference_mode()
     def profile_dominant_op(self, data: torch.Tensor, n_batches: int = 6):
@@ -337,7 +411,7 @@ class nnUNetPredictor(object):
         nf = len(flips)
         starts = sw.tile_starts(tuple(data.shape[1:]), patch, self.tile_step_size)
         tpb = self._choose_tiles_per_batch(nf, len(starts))
-        eng = self.network.engine(self.device, tpb * nf)
+        eng = self.network.engine(self.device, max(self._engine_capacity(nf), tpb * nf))
         prog = eng.program
         flops = [o.flops(prog.buffers[o.src][0], prog.buffers[o.dst][0]) for o in prog.ops]
         idx = int(np.argmax(flops))
@@ -383,7 +457,8 @@ class nnUNetPredictor(object):
 
     @torch.inference_mode()
     def _internal_predict_sliding_window_return_logits(self, data: torch.Tensor, slicers,
-                                                       do_on_device: bool = True, return_labels: bool = False):
+                                                       do_on_device: bool = True, return_labels: bool = False,
+                                                       all_folds: bool = False):
         if not do_on_device:
             raise RuntimeError('the B200 engine keeps the result arrays on the device; there is no CPU results path')
         patch = tuple(self.configuration_manager.patch_size)
@@ -394,19 +469,19 @@ class nnUNetPredictor(object):
         if self.collect_timing:
             self.timing['_volumes'] = self.timing.get('_volumes', 0) + 1
         acc = torch.zeros((heads, *vol), dtype=self.accumulator_dtype, device=self.device)
-        self._sliding_window_accumulate(data, starts, acc)
+        self._sliding_window_accumulate(data, starts, acc, all_folds=all_folds)
         self._mark('weight_sum')
-        wsum = torch.empty(vol, dtype=self.accumulator_dtype, device=self.device)
-        steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
-        E.weight_sum(steps, patch, self._gaussian(patch), wsum)
+        n_folds = len(self.list_of_parameters) if (all_folds and self.list_of_parameters) else 1
+        m0 = E.mem_launches()
+        wsum = self._weight_sum(vol, patch, scale=float(n_folds), dtype=self.accumulator_dtype)
         self._mark('finalize')
         inf_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         logits = None if return_labels == 'only' else torch.empty((heads, *vol), dtype=torch.float16, device=self.device)
         labels = torch.empty(vol, dtype=torch.uint8, device=self.device) if return_labels else None
         E.finalize(acc, wsum, logits, labels, inf_flag)
         self._mark(None)
-        self.last_launches += 2
-        del acc, wsum
+        self.last_launches += 1 + (E.mem_launches() - m0)
+        del acc
         if int(inf_flag.item()) != 0:
             raise RuntimeError('Encountered inf in predicted array. Aborting... If this problem persists, '
                                'reduce value_scaling_factor in compute_gaussian or increase the dtype of '
@@ -433,7 +508,7 @@ class nnUNetPredictor(object):
         return data.contiguous(), slicer
 
     @torch.inference_mode()
-    def predict_sliding_window_return_logits(self, input_image: torch.Tensor) -> torch.Tensor:
+    def predict_sliding_window_return_logits(self, input_image: torch.Tensor, *, _all_folds: bool = False) -> torch.Tensor:
         self._check_ready(input_image)
         self.network = self.network.to(self.device)
         self.network.eval()
@@ -445,7 +520,8 @@ class nnUNetPredictor(object):
         with torch.cuda.device(self.device):
             data, slicer_revert_padding = self._pad(input_image)
             slicers = self._internal_get_sliding_window_slicers(data.shape[1:])
-            predicted_logits = self._internal_predict_sliding_window_return_logits(data, slicers, True)
+            predicted_logits = self._internal_predict_sliding_window_return_logits(data, slicers, True,
+                                                                                   all_folds=_all_folds)
             predicted_logits = predicted_logits[(slice(None), *slicer_revert_padding)]
         return predicted_logits
 
@@ -483,8 +559,14 @@ class nnUNetPredictor(object):
         patch = tuple(self.configuration_manager.patch_size)
         heads = self.label_manager.num_segmentation_heads
         with torch.cuda.device(self.device):
-            data, revert = self._pad(input_image)
-            vol = tuple(data.shape[1:])
+            below, above = sw.pad_amounts(input_image.shape[1:], patch)
+            padded = any(b or a for b, a in zip(below, above))
+            if padded or input_image.device.type == 'cuda':
+                data, revert = self._pad(input_image)            # tiny volume (or already resident): whole volume
+                vol = tuple(data.shape[1:])
+            else:
+                data, vol = None, tuple(int(v) for v in input_image.shape[1:])
+                revert = tuple(slice(0, v) for v in vol)
             starts = sw.tile_starts(vol, patch, self.tile_step_size)
             plan = sharding.plan_shards(starts, patch, vol, world)
             lo, hi = plan.tile_ranges[rank]
@@ -494,17 +576,25 @@ class nnUNetPredictor(object):
                 self.timing['_volumes'] = self.timing.get('_volumes', 0) + 1
             acc = torch.zeros((heads, l1 - l0, vol[1], vol[2]), dtype=torch.float32, device=self.device)
             if hi > lo:
-                self._sliding_window_accumulate(data, starts[lo:hi], acc, acc_origin=(l0, 0, 0))
+                if data is None:
+                    # host input: upload only the planes this rank's tiles read (slab), not the whole volume
+                    s0, s1 = plan.slabs[rank]
+                    part = input_image[:, s0:s1]
+                    if not part.is_pinned():
+                        part = part.contiguous()
+                    slab = part.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+                    self._sliding_window_accumulate(slab, starts[lo:hi], acc, acc_origin=(l0, 0, 0),
+                                                    data_origin=(s0, 0, 0))
+                else:
+                    self._sliding_window_accumulate(data, starts[lo:hi], acc, acc_origin=(l0, 0, 0))
             self._mark('exchange')
             sharding.exchange_halos(acc, plan, rank, E.add_inplace, group)
             self._mark('weight_sum')
             n_own = o1 - o0
             out = None
             if n_own > 0:
-                wsum = torch.empty((n_own, vol[1], vol[2]), dtype=torch.float32, device=self.device)
-                steps = sw.compute_steps_for_sliding_window(vol, patch, self.tile_step_size)
-                steps = [[s - o0 for s in steps[0]], steps[1], steps[2]]
-                E.weight_sum(steps, patch, self._gaussian(patch), wsum)
+                m0 = E.mem_launches()
+                wsum = self._weight_sum(vol, patch, x_offset=o0, n_planes=n_own)
                 self._mark('finalize')
                 inf_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
                 view = acc[:, o0 - l0:o1 - l0]
@@ -514,7 +604,7 @@ class nnUNetPredictor(object):
                 else:
                     out = torch.empty((heads, n_own, vol[1], vol[2]), dtype=torch.float16, device=self.device)
                     E.finalize(view, wsum, out, None, inf_flag)
-                self.last_launches += 2
+                self.last_launches += 1 + (E.mem_launches() - m0)
                 if int(inf_flag.item()) != 0:
                     raise RuntimeError('Encountered inf in predicted array.')
             self._mark('gather_result')
@@ -538,16 +628,16 @@ class nnUNetPredictor(object):
                         else:
                             full[:, a:b] = out
                     elif return_labels:
-                        ops.append(dist.P2POp(dist.irecv, full[a:b], r, group=group))
+                        ops.append(dist.P2POp(dist.irecv, full[a:b], sharding.global_rank(group, r), group=group))
                     else:
                         for h in range(heads):
-                            ops.append(dist.P2POp(dist.irecv, full[h, a:b], r, group=group))
+                            ops.append(dist.P2POp(dist.irecv, full[h, a:b], sharding.global_rank(group, r), group=group))
             elif n_own > 0:
                 if return_labels:
-                    ops.append(dist.P2POp(dist.isend, out, gather_to, group=group))
+                    ops.append(dist.P2POp(dist.isend, out, sharding.global_rank(group, gather_to), group=group))
                 else:
                     for h in range(heads):
-                        ops.append(dist.P2POp(dist.isend, out[h], gather_to, group=group))
+                        ops.append(dist.P2POp(dist.isend, out[h], sharding.global_rank(group, gather_to), group=group))
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
@@ -557,20 +647,29 @@ class nnUNetPredictor(object):
             return out
 
     @torch.inference_mode()
-    def predict_logits_from_preprocessed_data(self, data: torch.Tensor) -> torch.Tensor:
-        """Fold loop of the reference (:471-504); returns the fold-averaged logits on the CPU."""
-        prediction = None
-        for params in self.list_of_parameters:
-            self.network.load_state_dict(params)
-            if prediction is None:
-                prediction = self.predict_sliding_window_return_logits(data).to('cpu')
-            else:
-                prediction += self.predict_sliding_window_return_logits(data).to('cpu')
-        if len(self.list_of_parameters) > 1:
-            prediction /= len(self.list_of_parameters)
+    def predict_logits_from_preprocessed_data(self, data: torch.Tensor, *, on_device: bool = False) -> torch.Tensor:
+        """Fold ensemble of the reference (:471-504).  The reference runs the whole sliding window once per fold,
+        copies every fold's logits to the CPU and averages there; here every fold's engine is resident, all folds
+        run on each gathered tile batch and are summed into ONE accumulator on the device (mean over folds = the
+        weight sum times the fold count), and the result is returned on the CPU like the reference's
+        (`on_device=True` leaves it on the GPU for the export step)."""
+        n_folds = len(self.list_of_parameters) if self.list_of_parameters else 1
+        if n_folds > 1 and self.accumulator_dtype == torch.float32:
+            prediction = self.predict_sliding_window_return_logits(data, _all_folds=True)
+        else:
+            prediction = None
+            for params in (self.list_of_parameters or [None]):
+                if params is not None:
+                    self.network.load_state_dict(params)
+                if prediction is None:
+                    prediction = self.predict_sliding_window_return_logits(data)
+                else:
+                    prediction += self.predict_sliding_window_return_logits(data)
+            if n_folds > 1:
+                prediction /= n_folds
         if self.verbose:
             print('Prediction done')
-        return prediction
+        return prediction if on_device else prediction.to('cpu')
 
     def predict_single_npy_array(self, input_image: np.ndarray, image_properties: dict,
                                  segmentation_previous_stage: np.ndarray = None,

@@ -24,6 +24,31 @@ from . import _lib
 LRELU_SLOPE = 0.01   # torch.nn.LeakyReLU default; plans carry nonlin_kwargs {'inplace': True} only
 
 
+class UnsupportedArchitecture(RuntimeError):
+    pass
+
+
+def check_arch(arch_kwargs: dict) -> float:
+    """The engine fuses InstanceNorm(affine) + LeakyReLU/ReLU; the reference builds whatever the plans say
+    (utilities/get_network_from_plans.py:17-38).  Anything else is refused here, loudly, instead of producing
+    silently different logits.  Dropout is the identity in eval mode, the only mode on this path.
+    Returns the activation's negative slope."""
+    def name(v):
+        return v if isinstance(v, str) else getattr(v, '__name__', str(v))
+    norm = name(arch_kwargs.get('norm_op') or 'InstanceNorm3d')
+    if not norm.endswith('InstanceNorm3d'):
+        raise UnsupportedArchitecture(f'unsupported architecture: norm_op={norm!r} (the B200 engine fuses InstanceNorm3d only)')
+    if not (arch_kwargs.get('norm_op_kwargs') or {}).get('affine', True):
+        raise UnsupportedArchitecture('unsupported architecture: norm_op_kwargs.affine=False')
+    nonlin = name(arch_kwargs.get('nonlin') or 'LeakyReLU')
+    kw = arch_kwargs.get('nonlin_kwargs') or {}
+    if nonlin.endswith('LeakyReLU'):
+        return float(kw.get('negative_slope', LRELU_SLOPE))
+    if nonlin.split('.')[-1] == 'ReLU':
+        return 0.0
+    raise UnsupportedArchitecture(f'unsupported architecture: nonlin={nonlin!r} (LeakyReLU and ReLU are supported)')
+
+
 @dataclass
 class Op:
     op: int
@@ -100,6 +125,13 @@ def clean_state_dict(sd: Dict) -> Dict:
     return out
 
 
+def padded_heads(num_heads: int) -> int:
+    for c in (2, 4, 8):
+        if num_heads <= c:
+            return c
+    return (num_heads + 15) // 16 * 16
+
+
 def _t3(v):
     if isinstance(v, int):
         return (v, v, v)
@@ -113,7 +145,8 @@ def _conv_out(dims, kernel, stride):
 
 
 class _Builder:
-    def __init__(self, sd, patch_size, in_channels, num_heads, conv_bias, eps):
+    def __init__(self, sd, patch_size, in_channels, num_heads, conv_bias, eps, slope):
+        self.slope = slope
         self.sd = sd
         self.p = Program(in_channels=in_channels, num_heads=num_heads, patch_size=tuple(patch_size))
         self.conv_bias = conv_bias
@@ -155,14 +188,16 @@ def _decoder(b: _Builder, feats, kernels, strides, stage_dims, skip_bufs, bottle
         src, cin = cat, 2 * c
         for j in range(n_conv_dec[l]):
             dst = p.add_buffer(stage_dims[s], c)
-            b.conv_norm(f'decoder.stages.{l}.convs.{j}', src, 0, cin, c, kernels[s], (1, 1, 1), dst, 0, LRELU_SLOPE)
+            b.conv_norm(f'decoder.stages.{l}.convs.{j}', src, 0, cin, c, kernels[s], (1, 1, 1), dst, 0, b.slope)
             src, cin = dst, c
         low, low_c = src, c
     # highest-resolution seg layer only (deep supervision off: UNetDecoder.forward uses seg_layers[-1])
     last = n_stages - 2
     w = b.get(f'decoder.seg_layers.{last}.weight')
     assert w.shape[:2] == (num_heads, feats[0]), f'seg layer weight {w.shape}'
-    out = p.add_buffer(stage_dims[0], num_heads)
+    # heads are padded per voxel to 2 / 4 / 8 / a multiple of 16 fp16 values so that the accumulate kernel reads a
+    # voxel's heads with one aligned 4 / 8 / 16 / 32-byte load (padding channels are never read back)
+    out = p.add_buffer(stage_dims[0], padded_heads(num_heads))
     p.ops.append(Op(op=_lib.OP_CONV, src=low, dst=out, cin=feats[0], cout=num_heads, kernel=(1, 1, 1),
                     stride=(1, 1, 1), weight=w, bias=b.get(f'decoder.seg_layers.{last}.bias'),
                     name=f'decoder.seg_layers.{last}'))
@@ -180,7 +215,8 @@ def build_plain_conv_unet(state_dict, arch_kwargs, in_channels, num_heads, patch
     n_dec = arch_kwargs['n_conv_per_stage_decoder']
     n_dec = [n_dec] * (n_stages - 1) if isinstance(n_dec, int) else list(n_dec)
     eps = float((arch_kwargs.get('norm_op_kwargs') or {}).get('eps', 1e-5))
-    b = _Builder(sd, patch_size, in_channels, num_heads, bool(arch_kwargs.get('conv_bias', False)), eps)
+    b = _Builder(sd, patch_size, in_channels, num_heads, bool(arch_kwargs.get('conv_bias', False)), eps,
+                 check_arch(arch_kwargs))
     p = b.p
     p.input_buffer = p.add_buffer(patch_size, in_channels)
     dims = tuple(patch_size)
@@ -200,7 +236,7 @@ def build_plain_conv_unet(state_dict, arch_kwargs, in_channels, num_heads, patch
             else:
                 dst, dst_coff = p.add_buffer(out_dims, c), 0
             b.conv_norm(f'encoder.stages.{s}.0.convs.{j}', src, src_coff, cin, c, kernels[s],
-                        strides[s] if j == 0 else (1, 1, 1), dst, dst_coff, LRELU_SLOPE)
+                        strides[s] if j == 0 else (1, 1, 1), dst, dst_coff, b.slope)
             src, src_coff, cin = dst, dst_coff, c
         skip_bufs.append(cat)
         dims = out_dims
@@ -221,13 +257,14 @@ def build_residual_encoder_unet(state_dict, arch_kwargs, in_channels, num_heads,
     n_dec = arch_kwargs['n_conv_per_stage_decoder']
     n_dec = [n_dec] * (n_stages - 1) if isinstance(n_dec, int) else list(n_dec)
     eps = float((arch_kwargs.get('norm_op_kwargs') or {}).get('eps', 1e-5))
-    b = _Builder(sd, patch_size, in_channels, num_heads, bool(arch_kwargs.get('conv_bias', False)), eps)
+    b = _Builder(sd, patch_size, in_channels, num_heads, bool(arch_kwargs.get('conv_bias', False)), eps,
+                 check_arch(arch_kwargs))
     p = b.p
     p.input_buffer = p.add_buffer(patch_size, in_channels)
     dims = tuple(patch_size)
     stem = p.add_buffer(dims, feats[0])
     b.conv_norm('encoder.stem.convs.0', p.input_buffer, 0, in_channels, feats[0], kernels[0], (1, 1, 1), stem, 0,
-                LRELU_SLOPE)
+                b.slope)
     x, x_coff, cin = stem, 0, feats[0]
     stage_dims, skip_bufs = [], []
     for s in range(n_stages):
@@ -243,7 +280,7 @@ def build_residual_encoder_unet(state_dict, arch_kwargs, in_channels, num_heads,
             has_stride = any(i != 1 for i in stride)
             proj = cin != c
             t1 = p.add_buffer(out_dims, c)
-            b.conv_norm(pre + '.conv1', x, x_coff, cin, c, kernels[s], stride, t1, 0, LRELU_SLOPE)
+            b.conv_norm(pre + '.conv1', x, x_coff, cin, c, kernels[s], stride, t1, 0, b.slope)
             t2 = p.add_buffer(out_dims, c)
             b.conv_norm(pre + '.conv2', t1, 0, c, c, kernels[s], (1, 1, 1), t2, 0, 1.0)
             r, r_coff = x, x_coff
@@ -264,7 +301,7 @@ def build_residual_encoder_unet(state_dict, arch_kwargs, in_channels, num_heads,
             else:
                 dst, dst_coff = p.add_buffer(out_dims, c), 0
             p.ops.append(Op(op=_lib.OP_ADD_ACT, src=t2, src2=r, src2_coff=r_coff, dst=dst, dst_coff=dst_coff, cin=c,
-                            cout=c, act_slope=LRELU_SLOPE, name=pre + '.add'))
+                            cout=c, act_slope=b.slope, name=pre + '.add'))
             x, x_coff, cin = dst, dst_coff, c
             del in_dims
         skip_bufs.append(cat)

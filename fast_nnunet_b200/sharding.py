@@ -94,6 +94,14 @@ def plan_shards(starts: np.ndarray, patch: Sequence[int], vol: Sequence[int], wo
     return ShardPlan(world, ranges, slabs, owned, local, transfers)
 
 
+def global_rank(group, group_rank: int) -> int:
+    """plan.transfers / gather_to hold ranks of `group`; torch.distributed's P2POp takes GLOBAL ranks."""
+    import torch.distributed as dist
+    if group is None or not dist.is_initialized():
+        return int(group_rank)
+    return int(dist.get_global_rank(group, int(group_rank)))
+
+
 def exchange_halos(acc, plan: ShardPlan, rank: int, add_fn: Callable, group=None):
     """acc: this rank's accumulator [H, local planes, Y, Z] (fp32).  Sends the planes other ranks own,
     receives the partial sums for the planes this rank owns and adds them with `add_fn(dst, src)`.
@@ -107,12 +115,12 @@ def exchange_halos(acc, plan: ShardPlan, rank: int, add_fn: Callable, group=None
     ops, recv_bufs = [], []
     for (_, dst, lo, hi) in plan.sends_of(rank):
         for h in range(H):
-            ops.append(dist.P2POp(dist.isend, acc[h, lo - l0:hi - l0], dst, group=group))
+            ops.append(dist.P2POp(dist.isend, acc[h, lo - l0:hi - l0], global_rank(group, dst), group=group))
     for (src, _, lo, hi) in plan.recvs_of(rank):
         for h in range(H):
             buf = torch.empty((hi - lo, *acc.shape[2:]), dtype=acc.dtype, device=acc.device)
             recv_bufs.append((h, lo, hi, buf))
-            ops.append(dist.P2POp(dist.irecv, buf, src, group=group))
+            ops.append(dist.P2POp(dist.irecv, buf, global_rank(group, src), group=group))
     nbytes = 0
     if ops:
         for w in dist.batch_isend_irecv(ops):

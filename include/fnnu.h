@@ -91,6 +91,11 @@ int fnnu_finalize(const void* acc, const void* wsum, int acc_dtype, int heads, c
  * gpu_launches evidence; fnnu_engine_launch_counts gives the network's). */
 long long fnnu_mem_launches(void);
 
+/* Fold ensembling (predict_from_raw_data.py:483-500: `prediction += ...; prediction /= n_folds`): every fold's
+ * tile predictions are accumulated into the SAME accumulator, so the fold mean is a division of the weight
+ * sum: x *= factor over n elements (fp32). */
+int fnnu_scale_inplace_f32(float* x, float factor, size_t n, void* stream);
+
 /* Multi-GPU halo step: acc += other over a contiguous range of n elements (fp32). */
 int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream);
 

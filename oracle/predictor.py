@@ -43,9 +43,10 @@ def accumulate_tiles(tile_predictions, slicers, volume_shape, num_heads, patch_s
                      acc_dtype=torch.half):
     """predict_from_raw_data.py:587-625 for already-computed per-tile predictions
     (list of (heads, *patch) tensors): fp16 accumulators, `pred *= g`, two `+=`, one `div`."""
-    logits = torch.zeros((num_heads, *volume_shape), dtype=acc_dtype)
-    n_pred = torch.zeros(volume_shape, dtype=acc_dtype)
-    g = gaussian_map(tuple(patch_size), 1. / 8, 10) if use_gaussian else 1
+    dev = tile_predictions[0].device       # CPU in the reference; the GPU box runs the same arithmetic faster
+    logits = torch.zeros((num_heads, *volume_shape), dtype=acc_dtype, device=dev)
+    n_pred = torch.zeros(volume_shape, dtype=acc_dtype, device=dev)
+    g = gaussian_map(tuple(patch_size), 1. / 8, 10).to(dev) if use_gaussian else 1
     for pred, sl in zip(tile_predictions, slicers):
         pred = pred.clone()
         if use_gaussian:

@@ -21,6 +21,11 @@ ROWS_W96 = dict(cls=M.PLAIN, in_ch=2, heads=2, patch=(12, 20, 96),
                 kw=M.plain_arch_kwargs([16, 32], [[1, 3, 3], [3, 3, 3]], [[1, 1, 1], [1, 2, 2]]))
 ROWS_W64_C32 = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(8, 24, 64),
                     kw=M.plain_arch_kwargs([32, 64], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
+# z-pair row-streaming kernel (conv_umma_zrows.cu): 3x3x3, Cout 16, even depth; W below 128, odd row counts, y segments
+ZROWS_W96 = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(6, 40, 96),
+                 kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
+ZROWS_W72_H9 = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(4, 18, 72),
+                    kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
 STUDENT = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
                kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
 

@@ -68,7 +68,10 @@ def test_accumulate_fp16_emulation_bit_exact(vol, patch, heads):
 
 
 @pytest.mark.parametrize('vol,patch,heads,pstride', [((64, 48, 64), (32, 32, 32), 2, 2), ((40, 48, 36), (32, 32, 32), 2, 2),
-                                                     ((33, 35, 41), (16, 24, 20), 3, 8), ((48, 32, 32), (32, 32, 32), 61, 64)])
+                                                     ((33, 35, 41), (16, 24, 20), 3, 8), ((48, 32, 32), (32, 32, 32), 61, 64),
+                                                     # cluster kernel variants: 4 / 8 / 16 heads per load, 2 or 4 z voxels
+                                                     ((48, 40, 48), (32, 32, 32), 4, 4), ((40, 40, 40), (32, 24, 32), 7, 8),
+                                                     ((40, 48, 38), (32, 32, 32), 25, 32), ((36, 36, 44), (24, 24, 24), 3, 4)])
 @pytest.mark.parametrize('chunk', [0, 4, 7])
 def test_accumulate_tta_fp32(vol, patch, heads, pstride, chunk):
     """fp16 predictions of 8 mirrored passes -> un-flip, mean, Gaussian weight, fp32 accumulate, normalise."""
@@ -135,6 +138,15 @@ def test_inf_is_flagged():
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
     E.finalize(acc, wsum, torch.empty((2, 8, 8, 8), dtype=torch.float16, device=DEV), None, flag)
     assert int(flag.item()) == 1
+
+
+def test_scale_inplace_and_launch_counter():
+    a = torch.randn(100003, device=DEV)
+    want = a * 3.0
+    n0 = E.mem_launches()
+    E.scale_inplace(a, 3.0)
+    assert torch.equal(a, want)
+    assert E.mem_launches() == n0 + 1
 
 
 def test_add_inplace():

@@ -30,7 +30,8 @@ def _run(spec, batch, backend, seed=0):
     return got, want, eng
 
 
-@pytest.mark.parametrize('name', ['SMALL_PLAIN', 'SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC', 'ROWS_W128', 'ROWS_W96', 'ROWS_W64_C32'])
+@pytest.mark.parametrize('name', ['SMALL_PLAIN', 'SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC', 'ROWS_W128', 'ROWS_W96', 'ROWS_W64_C32',
+                                  'ZROWS_W96', 'ZROWS_W72_H9'])
 @pytest.mark.parametrize('backend', [1, 0])
 def test_forward_matches_oracle(name, backend):
     spec = getattr(nets, name)
@@ -83,24 +84,45 @@ def test_intermediate_buffers_and_stats():
 
 
 def test_student_128_forward_matches_oracle():
-    """Full-size distilled student (r=2) on one 128^3 patch x 2 flips; the oracle side takes ~3 s on CPU."""
+    """Full-size distilled student (r=2), trained oracle weights (tests/nets.py: real margins, non-trivial
+    gamma / beta / bias), 128^3 phantom patches: north_star's label bar on every voxel."""
     spec = nets.STUDENT
-    sd, net = nets.make(spec, randomize_affine=False)
+    sd, net = nets.train_oracle(spec, steps=120, batch=1)
+    vol, _ = nets.phantom_volume((128, 128, 256), 1, 2, seed=11)
+    x = torch.stack([vol[:, :, :, :128], vol[:, :, :, 128:]])
+    cn = CompiledNetwork(spec['cls'], spec['kw'], 1, 2, spec['patch'])
+    cn.load_state_dict(sd)
+    got = cn(x.to(DEV)).float().cpu()
+    with torch.no_grad():
+        want = net.to(DEV)(x.half().float().to(DEV)).cpu()      # fp32 oracle network (TF32 off), on the GPU for speed
+    d = (got - want).abs()
+    agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+    rng = want.abs().max().item()
+    print(f'student128 (trained): max|d|={d.max():.4f} mean|d|={d.mean():.5f} range={rng:.2f} argmax agreement={agree:.6f}')
+    assert d.max().item() <= 0.06 * max(1.0, rng / 8) and d.mean().item() <= 0.006 * max(1.0, rng / 8)
+    assert agree >= 0.999
+
+
+def test_student_128_he_init_forward_matches_oracle():
+    """The same network with the reference's own initialisation (He-normal, gamma 1, beta 0): logits only, the two
+    class logits of every voxel are nearly tied, so label agreement is not a criterion here."""
+    spec = nets.STUDENT
+    sd, net = nets.make(spec, randomize_affine=True)
     g = torch.Generator().manual_seed(0)
     x = torch.randn((2, 1, 128, 128, 128), generator=g)
     cn = CompiledNetwork(spec['cls'], spec['kw'], 1, 2, spec['patch'])
     cn.load_state_dict(sd)
     got = cn(x.to(DEV)).float().cpu()
     with torch.no_grad():
-        want = net.to(DEV)(x.half().float().to(DEV)).cpu()      # fp32 oracle network, run on the GPU for speed
+        want = net.to(DEV)(x.half().float().to(DEV)).cpu()
     d = (got - want).abs()
-    agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
-    print(f'student128: max|d|={d.max():.4f} mean|d|={d.mean():.5f} range={want.abs().max():.2f} argmax agreement={agree:.5f}')
-    assert d.max().item() <= 0.15 and d.mean().item() <= 0.01
-    assert agree >= 0.99
+    rng = want.abs().max().item()
+    print(f'student128 (He init, random affine): max|d|={d.max():.4f} mean|d|={d.mean():.5f} range={rng:.2f}')
+    assert d.max().item() <= 0.15 * max(1.0, rng / 8) and d.mean().item() <= 0.01 * max(1.0, rng / 8)
 
 
-@pytest.mark.parametrize('name', ['SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC', 'ROWS_W128', 'ROWS_W96', 'ROWS_W64_C32'])
+@pytest.mark.parametrize('name', ['SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC', 'ROWS_W128', 'ROWS_W96', 'ROWS_W64_C32',
+                                  'ZROWS_W96', 'ZROWS_W72_H9'])
 def test_tcgen05_layers_match_direct_kernel(name):
     """Every activation buffer written with the tcgen05 implicit-GEMM back end against the CUDA-core direct
     kernel (same fp16 inputs, fp32 accumulation in both): differences are fp32 summation order + one fp16 ulp."""

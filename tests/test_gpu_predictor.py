@@ -10,7 +10,6 @@ from fast_nnunet_b200 import nnUNetPredictor
 from oracle import predictor as OP
 
 pytestmark = pytest.mark.gpu
-DEV = torch.device('cuda', 0)
 
 
 def _folder(tmp_path, spec, sd, **kw):
@@ -18,54 +17,24 @@ def _folder(tmp_path, spec, sd, **kw):
                                 spec['patch'], sd, spec['in_ch'], spec['heads'], **kw)
 
 
-def _oracle(net, x, patch, use_gaussian=True, mirror_axes=(0, 1, 2)):
-    """Reference arithmetic (fp16 accumulators) and the exact-accumulation variant from ONE set of oracle
-    tile predictions."""
-    _, tile_preds, slicers = OP.predict_sliding_window_return_logits(net, x, patch, 0.5, use_gaussian, mirror_axes,
-                                                                     return_tile_predictions=True)
-    xp, revert = OP.pad_to_patch(x, patch)
-    heads = tile_preds[0].shape[0]
-    ref16, n16 = OP.accumulate_tiles(tile_preds, slicers, tuple(xp.shape[1:]), heads, patch, use_gaussian, torch.half)
-    ref32, _ = OP.accumulate_tiles(tile_preds, slicers, tuple(xp.shape[1:]), heads, patch, use_gaussian, torch.float32)
-    crop = (slice(None), *revert[1:])
-    return ref16[crop], n16[tuple(revert[1:])], ref32[crop]
+from parity import DEV, compare as _compare, oracle_volume as _oracle  # noqa: E402
 
 
-def _compare(got_logits, oracle, heads, tol_max=0.06, tol_mean=0.006):
-    """Parity statement:
-      (1) against the oracle with exact (fp32) accumulation: max / mean |d| of the normalised logits on ALL voxels;
-      (2) against the reference arithmetic (fp16 accumulators): the same on the voxels whose weight sum is a normal
-          fp16 number (n_predictions >= 6.1e-5; below that the reference's own accumulators hold 1-2 significant bits);
-      (3) label agreement on all voxels, and on voxels whose top-2 margin exceeds 4 x tol_max it must be total."""
-    ref16, n16, ref32 = oracle
-    got = got_logits.float().cpu()
-    d32 = (got - ref32.float()).abs()
-    ok16 = (n16.float() >= 6.1e-5)
-    d16 = (got - ref16.float()).abs()[:, ok16]
-    seg_g, seg_32, seg_16 = (OP.logits_to_segmentation(t) for t in (got, ref32, ref16))
-    agree32 = float((seg_g == seg_32).mean())
-    agree16 = float((seg_g == seg_16)[ok16.numpy()].mean())
-    top2 = torch.topk(ref32.float(), 2, dim=0).values
-    confident = ((top2[0] - top2[1]) > 4 * tol_max).numpy()
-    agree_conf = float((seg_g == seg_32)[confident].mean()) if confident.any() else 1.0
-    dice = OP.dice_per_class(seg_g, seg_32, heads)
-    print(f'vs exact-acc oracle: max|d|={d32.max():.4f} mean|d|={d32.mean():.5f} labels agree={agree32:.5f} '
-          f'(confident {confident.mean():.3f} of voxels: {agree_conf:.6f}) dice={["%.4f" % v for v in dice]} | '
-          f'vs fp16-acc reference arithmetic on {float(ok16.float().mean()):.4f} of voxels: max|d|={d16.max():.4f} '
-          f'mean|d|={d16.mean():.5f} labels agree={agree16:.5f}')
-    assert d32.max().item() <= tol_max and d32.mean().item() <= tol_mean
-    assert d16.max().item() <= tol_max + 0.05 and d16.mean().item() <= tol_mean + 0.002
-    assert agree_conf == 1.0
-    assert agree32 >= 0.99
+TRAIN_STEPS = {'SMALL_PLAIN16': 200, 'SMALL_PLAIN': 200, 'SMALL_RESENC': 300, 'ANISO_PLAIN': 300}
+
+
+def _fixture(name):
+    spec = getattr(nets, name)
+    sd, net = nets.train_oracle(spec, steps=TRAIN_STEPS[name])
+    return spec, sd, net
 
 
 @pytest.mark.parametrize('name,vol', [('SMALL_PLAIN16', (48, 40, 56)), ('SMALL_RESENC', (40, 40, 40)),
                                       ('ANISO_PLAIN', (30, 40, 50))])
 def test_sliding_window_matches_oracle(tmp_path, name, vol):
-    spec = getattr(nets, name)
-    sd, net = nets.make(spec)
+    spec, sd, net = _fixture(name)
     folder = _folder(tmp_path, spec, sd)
-    x = nets.ct_like_volume(vol, spec['in_ch'])
+    x, _ = nets.phantom_volume(vol, spec['in_ch'], spec['heads'], seed=3)
     p = nnUNetPredictor(tile_step_size=0.5, use_gaussian=True, use_mirroring=True, device=DEV, allow_tqdm=False)
     p.initialize_from_trained_model_folder(folder, use_folds=(0,))
     got = p.predict_sliding_window_return_logits(x)
@@ -78,15 +47,14 @@ def test_sliding_window_matches_oracle(tmp_path, name, vol):
                                                               True, return_labels=True)
     assert np.array_equal(lb.cpu().numpy(), OP.logits_to_segmentation(lg).astype(np.uint8))
     labels = p.predict_sliding_window_return_segmentation(x)
-    assert float((labels.cpu().numpy() == OP.logits_to_segmentation(got)).mean()) >= 0.999
+    assert float((labels.cpu().numpy() == OP.logits_to_segmentation(got)).mean()) >= 0.9999
     assert p.last_launches > 0
 
 
 def test_small_volume_is_padded(tmp_path):
-    spec = nets.SMALL_PLAIN16
-    sd, net = nets.make(spec)
+    spec, sd, net = _fixture('SMALL_PLAIN16')
     folder = _folder(tmp_path, spec, sd)
-    x = nets.ct_like_volume((20, 33, 30), 1)
+    x, _ = nets.phantom_volume((20, 33, 30), 1, 2, seed=4)
     p = nnUNetPredictor(device=DEV, allow_tqdm=False)
     p.initialize_from_trained_model_folder(folder, use_folds=None)
     got = p.predict_sliding_window_return_logits(x)
@@ -95,10 +63,9 @@ def test_small_volume_is_padded(tmp_path):
 
 
 def test_no_mirroring_no_gaussian_and_fp16_accumulators(tmp_path):
-    spec = nets.SMALL_PLAIN16
-    sd, net = nets.make(spec)
+    spec, sd, net = _fixture('SMALL_PLAIN16')
     folder = _folder(tmp_path, spec, sd, mirror_axes=None)
-    x = nets.ct_like_volume((40, 40, 48), 1)
+    x, _ = nets.phantom_volume((40, 40, 48), 1, 2, seed=5)
     p = nnUNetPredictor(use_gaussian=False, use_mirroring=True, device=DEV, allow_tqdm=False,
                         accumulator_dtype=torch.float16, tiles_per_batch=3)
     p.initialize_from_trained_model_folder(folder, use_folds=(0,))
@@ -109,11 +76,11 @@ def test_no_mirroring_no_gaussian_and_fp16_accumulators(tmp_path):
 
 def test_fold_ensemble_and_cpu_return(tmp_path):
     spec = nets.SMALL_PLAIN
-    sd0, net0 = nets.make(spec, seed=1)
-    sd1, net1 = nets.make(spec, seed=2)
+    sd0, net0 = nets.train_oracle(spec, steps=200, seed=1)
+    sd1, net1 = nets.train_oracle(spec, steps=200, seed=2)
     folder = _folder(tmp_path, spec, sd0, fold=0)
     M.write_model_folder(folder, spec['cls'], spec['kw'], spec['patch'], sd1, 1, 2, fold=1)
-    x = nets.ct_like_volume((32, 40, 32), 1)
+    x, _ = nets.phantom_volume((32, 40, 32), 1, 2, seed=6)
     p = nnUNetPredictor(device=DEV, allow_tqdm=False)
     p.initialize_from_trained_model_folder(folder, use_folds=None)
     assert len(p.list_of_parameters) == 2
@@ -128,14 +95,13 @@ def test_fold_ensemble_and_cpu_return(tmp_path):
 def test_manual_initialization_with_live_module(tmp_path):
     from fast_nnunet_b200.plans import PlansManager, load_json
     import os
-    spec = nets.SMALL_PLAIN16
-    sd, net = nets.make(spec)
+    spec, sd, net = _fixture('SMALL_PLAIN16')
     folder = _folder(tmp_path, spec, sd)
     pm = PlansManager(load_json(os.path.join(folder, 'plans.json')))
     dj = load_json(os.path.join(folder, 'dataset.json'))
     p = nnUNetPredictor(device=DEV, allow_tqdm=False, use_mirroring=False)
     p.manual_initialization(net, pm, pm.get_configuration('3d_fullres'), None, dj, 'nnUNetTrainer', (0, 1, 2))
-    x = nets.ct_like_volume((32, 32, 48), 1)
+    x, _ = nets.phantom_volume((32, 32, 48), 1, 2, seed=8)
     got = p.predict_sliding_window_return_logits(x)
     _compare(got, _oracle(net, x.half().float(), spec['patch'], True, None), 2)
 
