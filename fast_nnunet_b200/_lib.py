@@ -55,6 +55,8 @@ _SIGNATURES = {
     'fnnu_finalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     'fnnu_mem_launches': (C.c_longlong, []),
+    'fnnu_export_labels': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     'fnnu_scale_inplace_f32': (C.c_int, [C.c_void_p, C.c_float, C.c_size_t, C.c_void_p]),
     'fnnu_add_inplace_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fnnu_engine_sizes': (C.c_int, [C.POINTER(BufferDesc), C.c_int, C.POINTER(OpDesc), C.c_int, C.c_int,

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libfnnu.so')
 OBJ = os.path.join(HERE, 'csrc', '_build')
-SOURCES = ['engine.cu', 'mem_kernels.cu', 'conv_ref.cu', 'conv_umma.cu', 'conv_umma_rows.cu', 'conv_umma_zrows.cu',
+SOURCES = ['engine.cu', 'mem_kernels.cu', 'export_kernels.cu', 'conv_ref.cu', 'conv_umma.cu', 'conv_umma_rows.cu', 'conv_umma_zrows.cu',
            'conv_first_umma.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

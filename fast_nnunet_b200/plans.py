@@ -90,6 +90,21 @@ class ConfigurationManager(object):
         return self.configuration['use_mask_for_norm']
 
     @property
+    def resampling_fn_data_kwargs(self) -> dict:
+        return dict(self.configuration.get('resampling_fn_data_kwargs') or
+                    {'is_seg': False, 'order': 3, 'order_z': 0, 'force_separate_z': None})
+
+    @property
+    def resampling_fn_seg_kwargs(self) -> dict:
+        return dict(self.configuration.get('resampling_fn_seg_kwargs') or
+                    {'is_seg': True, 'order': 1, 'order_z': 0, 'force_separate_z': None})
+
+    @property
+    def resampling_fn_probabilities_kwargs(self) -> dict:
+        return dict(self.configuration.get('resampling_fn_probabilities_kwargs') or
+                    {'is_seg': False, 'order': 1, 'order_z': 0, 'force_separate_z': None})
+
+    @property
     def network_arch_class_name(self) -> str:
         return self.configuration['architecture']['network_class_name']
 

@@ -675,15 +675,18 @@ class nnUNetPredictor(object):
                                  segmentation_previous_stage: np.ndarray = None,
                                  output_file_truncated: str = None,
                                  save_or_return_probabilities: bool = False):
-        """Array-in / label-map-out entry (:423-468).  Pre- and post-processing around the hot path are
-        host-side steps outside this engine's scope; the subset implemented in
-        `fast_nnunet_b200.prepost` covers images already at the plans' spacing."""
-        from . import prepost
+        """Array-in / label-map-out entry (:423-468).  Pre-processing, the fold ensemble and the
+        export to the image's own geometry (§8 f1) run on the device: the raw image goes up once, one uint8 per voxel
+        comes back.  Writing files (`output_file_truncated`) is outside the inference path."""
+        from . import export, preprocess
         if output_file_truncated is not None:
             raise NotImplementedError('file export is outside the B200 inference path (SURVEY.md §8 f1)')
-        data, props = prepost.preprocess_npy(input_image, image_properties, segmentation_previous_stage,
-                                             self.plans_manager, self.configuration_manager, self.dataset_json,
-                                             self.label_manager)
-        logits = self.predict_logits_from_preprocessed_data(torch.from_numpy(data))
-        return prepost.logits_to_segmentation_with_correct_shape(logits, props, self.plans_manager,
-                                                                 self.label_manager, save_or_return_probabilities)
+        E.require_cuda_device(self.device)
+        with torch.cuda.device(self.device):
+            data, props = preprocess.run_case_npy(input_image, image_properties, segmentation_previous_stage,
+                                                  self.plans_manager, self.configuration_manager, self.dataset_json,
+                                                  self.label_manager, self.device)
+            logits = self.predict_logits_from_preprocessed_data(data, on_device=True)
+            return export.convert_predicted_logits_to_segmentation_with_correct_shape(
+                logits, self.plans_manager, self.configuration_manager, self.label_manager, props,
+                save_or_return_probabilities, to_host=self.to_host)

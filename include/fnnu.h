@@ -100,6 +100,21 @@ int fnnu_scale_inplace_f32(float* x, float factor, size_t n, void* stream);
 int fnnu_add_inplace_f32(float* acc, const float* other, size_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Export: logits -> label map in the ORIGINAL image geometry (inference/export_prediction.py:14-71)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces convert_predicted_logits_to_segmentation_with_correct_shape for non-region label maps:
+ * resampling_fn_probabilities (default_resampling.py:89-192: order 1; order 0 along `nearest_axis` axes, the
+ * reference's "separate z" branch) of the fp16 logits [heads][in_dims] to `mid_dims`
+ * (shape_after_cropping_and_before_resampling), rounding to fp16 like the reference's output array, argmax (first
+ * maximum), insert_crop_into_image at bbox_lo into a zero canvas of canvas_dims (shape_before_cropping) and
+ * `.transpose(transpose_backward)`.  labels_out: uint8, dense, extents canvas_dims permuted by
+ * transpose_backward.  All arrays are in the transposed (network) axis order. */
+int fnnu_export_labels(const void* logits, int heads, const int in_dims[3], const int mid_dims[3],
+                       const int nearest_axis[3], const int bbox_lo[3], const int canvas_dims[3],
+                       const int transpose_backward[3], uint8_t* labels_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-patch network forward (replaces `self.network(x)`, :543/:555; PlainConvUNet /
  * ResidualEncoderUNet of dynamic_network_architectures as built by get_network_from_plans.py:9-43)
  * ---------------------------------------------------------------------------------------------- */
