@@ -25,10 +25,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# ncu --set full on the dominant launch, conv_umma_rows_kernel<16,2> = dec5.0 with 32 patches
-# (profiles/r01_ncu_final_rows_dec5.txt): dram read 5.070 GB + write 2.121 GB for 4.295 + 2.147 GB algorithmic
-# -> measured DRAM traffic / algorithmic bytes (the 18 % extra reads are z-neighbour planes that missed L2)
-NCU_TRAFFIC_OVER_ALGORITHMIC = (5.0698 + 2.1215) / (4.2950 + 2.1475)
+# `roofline.traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the dominant
+# kernel (same kernel, same patches per launch), written by tools/ncu_traffic.py into profiles/; null when the
+# committed capture does not match the kernel this run measured.
+TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')
 # bounded CPU samples: ~3.3 s per 128^3 student tile x 8 passes on 16 cores
 CPU_BASELINE_TILES = 4      # cpu_baseline of our arm: ~13 s of CPU work
 REF_TILES_PER_STEP = int(os.environ.get('FNNU_BENCH_REF_TILES', '3'))   # --impl reference: ~10 s per step
@@ -193,12 +193,70 @@ def run_reference(args, wl):
 
 
 def _conv_kernel_name(dom):
-    """Which tcgen05 kernel the engine picks for a stride-1 3x3x3 conv (mirrors plan_rows in conv_umma_rows.cu): the
-    row-streaming kernel for Cin in {16, 32}, Cout <= 32 and 64 <= W <= 128, else the general implicit GEMM."""
+    """Which tcgen05 kernel the engine picks for a stride-1 conv (mirrors plan_zrows / plan_rows in csrc/): the z-pair
+    row-streaming kernel for 3x3x3, Cin in {16, 32}, Cout <= 16, even depth, 64 <= W <= 128; the ky-folded
+    row-streaming kernel for Cout <= 32 otherwise; else the general implicit GEMM."""
     cout_pad = (dom['cout'] + 15) // 16 * 16
-    w = dom['out_dims'][2]
-    rows = dom['cin'] in (16, 32) and cout_pad in (16, 32) and 64 <= w <= 128
-    return 'conv_umma_rows_kernel' if rows else 'conv_umma_kernel'
+    d, _, w = dom['out_dims']
+    k = tuple(dom.get('kernel', (3, 3, 3)))
+    thin = dom['cin'] in (16, 32) and 64 <= w <= 128 and k[1:] == (3, 3)
+    if thin and k == (3, 3, 3) and cout_pad == 16 and d % 2 == 0 and os.environ.get('FNNU_ZROWS', '1') != '0':
+        return 'conv_umma_zrows_kernel'
+    if thin and cout_pad in (16, 32):
+        return 'conv_umma_rows_kernel'
+    return 'conv_umma_kernel'
+
+
+def _ncu_traffic(kernel, patches, op_name):
+    """Bytes of DRAM traffic per launch from the committed ncu capture of the SAME kernel and patch count."""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+    except Exception:
+        return None
+    for e in d.get('captures', []):
+        if e.get('kernel') == kernel and e.get('op') == op_name and e.get('patches_per_launch') == patches:
+            return float(e['dram_bytes_read'] + e['dram_bytes_write'])
+    return None
+
+
+def torch_gpu_baseline(wl, dev, n_tiles_sample=6):
+    """The reference's own CUDA path as BASELINE.md section 3 describes it: the network under
+    torch.autocast('cuda') fp16 with cudnn.benchmark (predict_from_raw_data.py:60, :648), batch 1, eight sequential
+    mirror passes per tile (:541-557), Gaussian-weighted fp16 accumulation (:587-620) — the oracle's restatement of that
+    loop, run on THIS GPU over a sub-volume holding `n_tiles_sample` tiles, extrapolated by tile count."""
+    from fast_nnunet_b200 import model_folder as M
+    from fast_nnunet_b200 import sliding_window as sw
+    from oracle import networks as N
+    from oracle import predictor as OP
+    vol, feats, ks, ss, patch, heads = WORKLOADS[wl][:6]
+    blocks = WORKLOADS[wl][7] if len(WORKLOADS[wl]) > 7 else None
+    cls = M.RESENC if blocks else M.PLAIN
+    kw = M.resenc_arch_kwargs(feats, ks, ss, blocks) if blocks else M.plain_arch_kwargs(feats, ks, ss)
+    sd = M.synthesize_state_dict(cls, kw, vol[0], heads, seed=1234)
+    net = N.build_from_arch(cls, kw, vol[0], heads, allow_init=False)
+    net.load_state_dict(sd)
+    net.eval().to(dev)
+    n_total = len(sw.tile_starts(vol[1:], patch, 0.5))
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    x = synth_volume((vol[0], patch[0], patch[1], patch[2] + (n_tiles_sample - 1) * (patch[2] // 2)), 0).to(dev)
+    try:
+        for _ in range(2):      # warm-up incl. cuDNN autotuning
+            OP.predict_sliding_window_return_logits(net, x, patch, 0.5, True, (0, 1, 2), autocast_device='cuda')
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        OP.predict_sliding_window_return_logits(net, x, patch, 0.5, True, (0, 1, 2), autocast_device='cuda')
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        torch.backends.cudnn.benchmark = old
+        del net, x
+        torch.cuda.empty_cache()
+    spv = dt / n_tiles_sample * n_total
+    return {'sec_per_volume': spv, 'value': float(np.prod(vol[1:])) / spv / 1e6, 'unit': 'Mvoxel/s',
+            'what': "oracle restatement of the reference's CUDA path: torch.autocast('cuda') fp16, cudnn.benchmark=True, "
+                    'batch 1, 8 sequential mirror passes per tile, fp16 accumulators, on this GPU',
+            'sample': f'{n_tiles_sample} of {n_total} tiles ({dt:.2f} s), extrapolated by tile count'}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -266,38 +324,43 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
-    # ---- e2e: the reference-facing call with HOST buffers (pinned input, logits returned on the CPU)
-    e2e_ms = None
-    h2d = d2h = 0
-    if world == 1:
-        for _ in range(1):
-            pred.predict_logits_from_preprocessed_data(host)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            res = pred.predict_logits_from_preprocessed_data(host)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
-        h2d = host.numel() * host.element_size()
-        d2h = res.numel() * res.element_size()
-        del res
-    else:
-        sync_all()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            d = host.to(dev, non_blocking=True)
-            lab = pred.predict_sliding_window_sharded(d, return_labels=True, gather_to=0)
-            if rank == 0:
-                lab_host = lab.cpu()
-        sync_all()
-        e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
-        h2d = host.numel() * host.element_size()
-        d2h = int(nvox) if rank == 0 else 0
+    # ---- e2e: HOST volume in (pinned) -> HOST label map out, the SAME call at every N (each rank uploads only the
+    # planes its tiles read; rank 0 downloads the uint8 label map through a pinned buffer); at N = 1 additionally the
+    # reference-facing logits call (host fp16 logits out) as `e2e_logits`
+    def e2e_step():
+        lab = pred.predict_sliding_window_sharded(host, return_labels=True, gather_to=0)
+        if rank == 0:
+            return pred.to_host(lab)
+        return None
+
+    e2e_step()
+    sync_all()
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
+    h2d = host.numel() * host.element_size()
+    d2h = int(nvox) if rank == 0 else 0
+    if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    e2e_logits = None
+    if world == 1 and heads <= 8:
+        pred.predict_logits_from_preprocessed_data(host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            res = pred.predict_logits_from_preprocessed_data(host)
+        torch.cuda.synchronize()
+        ms_l = (time.perf_counter() - t0) / n_e2e * 1e3
+        e2e_logits = {'value': nvox / (ms_l * 1e-3) / 1e6, 'unit': 'Mvoxel/s', 'sec_per_volume': ms_l * 1e-3,
+                      'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': res.numel() * res.element_size(),
+                      'call': 'predict_logits_from_preprocessed_data(host tensor) -> host fp16 logits (pageable, as the '
+                              'reference returns them)'}
+        del res
 
     dom = pred.profile_dominant_op(data) if rank == 0 else None
     if rank == 0:
@@ -314,8 +377,7 @@ def run_ours(args, wl):
         # capture of the same kernel class (profiles/README.md), scaled to this launch's patch count
         roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': peaks['bf16_tflops_sustained'],
                 'achieved': dom['flop_per_launch'] / (dom['ms'] * 1e-3) / 1e12,
-                'traffic': (dom['algorithmic_bytes_per_launch'] * NCU_TRAFFIC_OVER_ALGORITHMIC
-                            if _conv_kernel_name(dom) == 'conv_umma_rows_kernel' else None),
+                'traffic': _ncu_traffic(_conv_kernel_name(dom), dom['patches_per_launch'], dom['op']),
                 'algorithmic_bytes': dom['algorithmic_bytes_per_launch'],
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; fp16 runs at the same tcgen05 rate)',
                 'kernel': _conv_kernel_name(dom) + ' (' + dom['op'] + f", Conv3d {dom['cin']}->{dom['cout']} @{dom['out_dims']}"
@@ -329,8 +391,16 @@ def run_ours(args, wl):
         roof_all['frac'] = roof_all['achieved'] / roof_all['peak'] if roof_all['achieved'] else None
         roof_mem = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peaks['hbm_gbs'],
                     'achieved': (acc_bytes / (acc_ms * 1e-3) / 1e9) if acc_ms else None, 'traffic': None,
-                    'kernel': 'accumulate_h2_vec4_kernel', 'bytes_per_tile': acc_bytes * world / n_tiles}
+                    'kernel': 'accumulate_cluster_kernel (TTA mean + Gaussian weight + accumulate, one launch per group of '
+                              'overlapping tiles)', 'bytes_per_tile': acc_bytes * world / n_tiles}
         roof_mem['frac'] = roof_mem['achieved'] / roof_mem['peak'] if roof_mem['achieved'] else None
+        gpu_ref = None
+        if world == 1 and not args.no_torch_gpu_baseline:
+            try:
+                gpu_ref = torch_gpu_baseline(wl, dev)
+                gpu_ref['ours_over_torch_gpu'] = gpu_ref['sec_per_volume'] / (ms * 1e-3)
+            except Exception as e:        # a baseline, never a reason to lose the measurement
+                gpu_ref = {'unavailable': repr(e)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -350,8 +420,9 @@ def run_ours(args, wl):
                        'parallelism': f'x-slab tile sharding over {world} GPU(s), one halo exchange'},
             'e2e': {'value': nvox / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mvoxel/s', 'sec_per_volume': e2e_ms * 1e-3,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'call': 'predict_logits_from_preprocessed_data(host tensor) -> host fp16 logits' if world == 1
-                    else 'host volume -> predict_sliding_window_sharded -> host uint8 label map'},
+                    'call': 'pinned host volume -> predict_sliding_window_sharded(return_labels) -> pinned host uint8 label '
+                            'map (same call at every N)'},
+            'e2e_logits': e2e_logits, 'torch_gpu_baseline': gpu_ref,
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_network': roof_all,
             'roofline_aggregation': roof_mem,
             'phase_ms_per_volume': phase, 'cpu_baseline': cpu,
@@ -370,6 +441,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--tiles-per-batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-gpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args, args.workload)

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfnnu.so')
+LIB_PATH = os.environ.get('FNNU_LIB') or os.path.join(_HERE, 'libfnnu.so')     # FNNU_LIB: instrumented profiling builds
 
 OP_CONV, OP_TCONV, OP_ADD_ACT, OP_AVGPOOL = 0, 1, 2, 3
 ACC_F32, ACC_F16 = 0, 1
@@ -55,6 +55,17 @@ _SIGNATURES = {
     'fnnu_finalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_size_t, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     'fnnu_mem_launches': (C.c_longlong, []),
+    'fnnu_pre_nonzero_bbox': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    'fnnu_pre_filled_mask': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'fnnu_pre_channel_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    'fnnu_pre_crop_normalize': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fnnu_pre_resample_workspace_bytes': (C.c_size_t, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'fnnu_pre_resample_channel': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                            C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     'fnnu_export_labels': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     'fnnu_scale_inplace_f32': (C.c_int, [C.c_void_p, C.c_float, C.c_size_t, C.c_void_p]),

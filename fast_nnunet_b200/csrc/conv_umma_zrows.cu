@@ -27,13 +27,25 @@
 
 namespace fnnu {
 
+#ifdef FNNU_ZROWS_PROF
+// clock64 accounting per warp role of CTA 0 (temporary profiling builds only): [role * 8 + counter]
+__device__ long long g_zprof[32];
+#define ZPROF_T(var) const long long var = clock64()
+#define ZPROF_ADD(slot, expr) do { if (blockIdx.x == 0) zp[slot] += (expr); } while (0)
+#else
+#define ZPROF_T(var)
+#define ZPROF_ADD(slot, expr)
+#endif
+
 namespace {
 
-constexpr int kZProducerWarps = 12;
-constexpr int kZEpilogueWarp0 = 12;          // warps 12-15: plane z0, warps 16-19: plane z0 + 1
-constexpr int kZMmaWarp0 = 20;               // warps 20, 21 issue; 22, 23 only donate registers
-constexpr int kZThreads = 24 * 32;
-constexpr int kZRegsProducer = 88, kZRegsEpilogue = 88, kZRegsMma = 40;   // 384 x 88 + 256 x 88 + 128 x 40 = 768 x 80
+// The producers are bound by latency per warp (LDG -> transform -> STS, ~7 k cycles per stage and group of warps
+// measured with clock64), not by issue slots (46 % busy): 16 of them, i.e. 8 (Cin 16) or 4 (Cin 32) stages in flight.
+constexpr int kZProducerWarps = 16;
+constexpr int kZEpilogueWarp0 = 16;          // warps 16-19: plane z0, warps 20-23: plane z0 + 1
+constexpr int kZMmaWarp0 = 24;               // warps 24, 25 issue; 26, 27 only donate registers
+constexpr int kZThreads = 28 * 32;
+constexpr int kZRegsEpilogue = 88, kZRegsMma = 40;   // launch: 896 x 72; 512 x 72 + 256 x 88 + 128 x 40 = 896 x 72
 constexpr int kZProw = 140;                  // positions per (plane, 8-channel group): 1 + 128 + 1, padded to 4 (mod 8)
 constexpr int kZSlots = 5;                   // y-steps resident in TMEM: 5 x 96 columns
 constexpr int kZSlotCols = 96;
@@ -104,6 +116,10 @@ __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // y = lrelu((x - m) * s + t) on 8 fp16 channels, packed half2 arithmetic
@@ -182,7 +198,6 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
 
   if (warp < kZProducerWarps) {
     // =========================== PRODUCERS ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kZRegsProducer));
     const int grp = warp / kGroupWarps;
     const int wg = warp - grp * kGroupWarps;
     // a warp covers 16 positions x one PAIR of 8-channel groups (32 contiguous bytes per voxel), so "these channels
@@ -202,9 +217,15 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     const uint32_t my_off = (uint32_t)(q * kZProw + x0 + 1) * 16u;      // + it * 512
     const size_t row_bytes = (size_t)c.W * a.src_cs * 2;
     const size_t zplane_bytes = (size_t)c.H * row_bytes;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const bool full_w = c.W == 128;                          // every lane's four positions lie inside the row
     int t = 0, t_grp = 0, stage = 0;                         // step counter, its group, its stage
     int cur_b = -1;
     __half2 m2[4], s2[4], t2[4], l2[4];
+#ifdef FNNU_ZROWS_PROF
+    long long zp[4] = {0, 0, 0, 0};
+    const long long zt0 = clock64();
+#endif
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z0, ya, yb;
       decode(u, b, z0, ya, yb);
@@ -251,37 +272,86 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         if (!mine) continue;
         const int y_in = ya - 1 + j;
         const bool row_ok = y_in >= 0 && y_in < c.H;
-        uint8_t* st_base = ring + (size_t)my_stage * c.stage_bytes + my_off;
-        const char* row0 = vol0 + (size_t)(row_ok ? y_in : 0) * row_bytes + goff0;
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          uint4 v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int pl = hp * 2 + (k >> 2), it = k & 3;
-            v[k] = make_uint4(0, 0, 0, 0);
-            if (row_ok && ((pl_ok >> pl) & 1) && ((in_w >> it) & 1))
-              v[k] = ldg_nc16(row0 + (size_t)pl * zplane_bytes + it * gstep);
-          }
+        const uint32_t st = ring_u32 + (uint32_t)my_stage * (uint32_t)c.stage_bytes + my_off;
+        auto wait_stage_free = [&]() {
           // the loads do not need the stage: only the stores wait for its previous y-step to be consumed
-          if (hp == 0 && my_t >= c.stages) {
+          if (my_t >= c.stages) {
             const int tp = my_t - c.stages;
+            ZPROF_T(w0);
             mbar_wait(&step_bar[tp & (kZStepBars - 1)], (uint32_t)(tp >> 4) & 1u);
+            ZPROF_ADD(0, clock64() - w0);
           }
+        };
+        if (!row_ok) {
+          // a row outside the image: zeros (the conv's zero padding applies to the NORMALISED activations)
+          wait_stage_free();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int pl = hp * 2 + (k >> 2), it = k & 3;
-            if (((pl_ok >> pl) & 1) && ((in_w >> it) & 1)) {
-              uint4 o = v[k];
-              if (row_ok && !q_identity) o = zxform8(o, m2, s2, t2, l2);
-              *reinterpret_cast<uint4*>(st_base + pl * plane_bytes + it * 512) = o;
+          for (int pl = 0; pl < 4; ++pl)
+            if ((pl_ok >> pl) & 1) {
+#pragma unroll
+              for (int it = 0; it < 4; ++it)
+                if ((in_w >> it) & 1) sts16(st + pl * plane_bytes + it * 512, make_uint4(0, 0, 0, 0));
+            }
+        } else {
+          const char* row0 = vol0 + (size_t)y_in * row_bytes + goff0;
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            // two planes per round: 8 independent 16-byte loads in flight per thread; plane validity is CTA-uniform
+            const bool va = (pl_ok >> (2 * hp)) & 1, vb = (pl_ok >> (2 * hp + 1)) & 1;
+            const char* pa = row0 + (size_t)(2 * hp) * zplane_bytes;
+            const char* pb = pa + zplane_bytes;
+            uint4 v[8];
+            if (full_w) {
+              if (va) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) v[it] = ldg_nc16(pa + it * gstep);
+              }
+              if (vb) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) v[4 + it] = ldg_nc16(pb + it * gstep);
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                v[it] = make_uint4(0, 0, 0, 0);
+                v[4 + it] = make_uint4(0, 0, 0, 0);
+                if (va && ((in_w >> it) & 1)) v[it] = ldg_nc16(pa + it * gstep);
+                if (vb && ((in_w >> it) & 1)) v[4 + it] = ldg_nc16(pb + it * gstep);
+              }
+            }
+            if (hp == 0) wait_stage_free();
+            if (!q_identity) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = zxform8(v[k], m2, s2, t2, l2);
+            }
+            if (full_w) {
+              if (va) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) sts16(st + (2 * hp) * plane_bytes + it * 512, v[it]);
+              }
+              if (vb) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) sts16(st + (2 * hp + 1) * plane_bytes + it * 512, v[4 + it]);
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                if (va && ((in_w >> it) & 1)) sts16(st + (2 * hp) * plane_bytes + it * 512, v[it]);
+                if (vb && ((in_w >> it) & 1)) sts16(st + (2 * hp + 1) * plane_bytes + it * 512, v[4 + it]);
+              }
             }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_warp(&full_bar[my_stage]);
+        ZPROF_ADD(1, 1);
       }
     }
+#ifdef FNNU_ZROWS_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      g_zprof[0] = zp[0]; g_zprof[1] = zp[1]; g_zprof[2] = clock64() - zt0;
+    }
+#endif
   } else if (warp >= kZMmaWarp0) {
     // =========================== MMA ISSUERS ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kZRegsMma));
@@ -295,6 +365,10 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       mbar_wait(w_bar, 0);
       int t = 0, turn = 0, stage = 0, slot = 0;
       uint32_t phase = 0, sphase = 0;
+#ifdef FNNU_ZROWS_PROF
+      long long zp[4] = {0, 0, 0, 0};
+      const long long zt0 = clock64();
+#endif
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         int b, z0, ya, yb;
         decode(u, b, z0, ya, yb);
@@ -302,8 +376,13 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         const bool pl0 = z0 >= 1, pl3 = z0 + 2 < c.D;
         for (int j = 0; j < n_rows; ++j) {
           if (turn == me) {
+            ZPROF_T(w0);
             mbar_wait(&tempty_bar[slot], sphase ^ 1);
+            ZPROF_T(w1);
             mbar_wait(&full_bar[stage], phase);
+            ZPROF_T(w2);
+            ZPROF_ADD(0, w1 - w0);
+            ZPROF_ADD(1, w2 - w1);
             tc_fence_after();
             // lane-0 broadcasts tell ptxas the values are warp-uniform (uniform-register operands for UTCHMMA)
             const uint32_t d = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)slot * kZSlotCols, 0);
@@ -319,6 +398,8 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
             }
             __syncwarp();
+            ZPROF_ADD(2, clock64() - w2);
+            ZPROF_ADD(3, 1);
           }
           ++t;
           if (++turn == c.issuers) turn = 0;
@@ -326,6 +407,12 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
           if (++slot == kZSlots) { slot = 0; sphase ^= 1; }
         }
       }
+#ifdef FNNU_ZROWS_PROF
+      if (blockIdx.x == 0 && lane == 0) {
+        long long* o = g_zprof + 8 + me * 8;
+        o[0] = zp[0]; o[1] = zp[1]; o[2] = zp[2]; o[3] = zp[3]; o[4] = clock64() - zt0;
+      }
+#endif
     }
   } else {
     // =========================== EPILOGUE (set k = output plane z0 + k) ===========================
@@ -359,6 +446,10 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       }
     };
     int t = 0, slot_a = 0;                           // step / TMEM slot holding input row y-1 of the next output row
+#ifdef FNNU_ZROWS_PROF
+    long long zp[4] = {0, 0, 0, 0};
+    const long long zt0 = clock64();
+#endif
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int b, z0, ya, yb;
       decode(u, b, z0, ya, yb);
@@ -374,7 +465,10 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       __half* out_px = a.dst + (((size_t)b * c.D + z0 + k) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs;
       for (int yo = 0; yo < n_out; ++yo, out_px += out_row_stride) {
         const int tc = t + 2;
+        ZPROF_T(w0);
         mbar_wait(&step_bar[tc & (kZStepBars - 1)], (uint32_t)(tc >> 4) & 1u);
+        ZPROF_ADD(0, clock64() - w0);
+        ZPROF_ADD(1, 1);
         tc_fence_after();
         int slot_b = slot_a + 1;
         if (slot_b == kZSlots) slot_b = 0;
@@ -428,6 +522,12 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       }
     }
     flush_stats(cur_b);
+#ifdef FNNU_ZROWS_PROF
+    if (blockIdx.x == 0 && lane == 0 && wq == 0) {
+      long long* o = g_zprof + 24 + k * 4;
+      o[0] = zp[0]; o[1] = zp[1]; o[2] = clock64() - zt0;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -476,6 +576,12 @@ int launch_pack_weights_zrows(const float* w_dev, void* out, const ConvArgs& a, 
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }
+
+#ifdef FNNU_ZROWS_PROF
+extern "C" int fnnu_debug_zrows_prof(long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_zprof, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int launch_conv_zrows(const ConvArgs& a, cudaStream_t s) {
   ZArgs p;

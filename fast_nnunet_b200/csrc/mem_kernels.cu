@@ -31,70 +31,72 @@ struct FlipList {
   uint8_t m[8];
 };
 
+// grid: x = chunks of 256 over (y, z) of one tile plane, y = tile plane x, z = sample (tile * n_flips + flip):
+// no 64-bit division on the path (the index arithmetic used to cost more than the three memory operations).
 __global__ void __launch_bounds__(256) gather_tiles_kernel(
     const float* __restrict__ vol, int C, int X, int Y, int Z, const int32_t* __restrict__ starts,
     int n_tiles, int pX, int pY, int pZ, FlipList flips, int n_flips, __half* __restrict__ out, int cs) {
-  const size_t pvox = (size_t)pX * pY * pZ;
-  const size_t total = pvox * n_tiles * n_flips;
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(pY * pZ)) return;
+  const int y = (int)(idx / (uint32_t)pZ);
+  const int z = (int)(idx - (uint32_t)y * (uint32_t)pZ);
+  const int x = blockIdx.y;
+  const int n = blockIdx.z;
+  const int t = n / n_flips;
+  const int f = flips.m[n - t * n_flips];
+  const int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
+  const int gx = sx + ((f & 1) ? pX - 1 - x : x);
+  const int gy = sy + ((f & 2) ? pY - 1 - y : y);
+  const int gz = sz + ((f & 4) ? pZ - 1 - z : z);
   const size_t vstride = (size_t)X * Y * Z;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    size_t n = i / pvox;
-    size_t r = i - n * pvox;
-    int z = (int)(r % pZ);
-    int y = (int)((r / pZ) % pY);
-    int x = (int)(r / ((size_t)pZ * pY));
-    int t = (int)(n / n_flips);
-    int f = flips.m[n - (size_t)t * n_flips];
-    int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
-    int gx = sx + ((f & 1) ? pX - 1 - x : x);
-    int gy = sy + ((f & 2) ? pY - 1 - y : y);
-    int gz = sz + ((f & 4) ? pZ - 1 - z : z);
-    const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
-    __half* dst = out + i * cs;
-    for (int c = 0; c < C; ++c) dst[c] = __float2half_rn(__ldg(src + c * vstride));
-    for (int c = C; c < cs; ++c) dst[c] = __float2half_rn(0.f);
+  const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
+  __half* dst = out + (((size_t)n * pX + x) * pY * pZ + idx) * cs;
+  if (cs == 4 && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) {
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = c < C ? __ldg(src + c * vstride) : 0.f;
+    __half2 h[2] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3])};
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(h);
+    return;
   }
+  for (int c = 0; c < C; ++c) dst[c] = __float2half_rn(__ldg(src + c * vstride));
+  for (int c = C; c < cs; ++c) dst[c] = __float2half_rn(0.f);
 }
 
 // Single-channel volumes (CT): one thread converts 8 consecutive z voxels -> one 16-byte store.
-// Mirrored-z copies read the 8 source voxels in reverse.  Requires pZ % 8 == 0 and cs == 1.
+// Mirrored-z copies read the 8 source voxels in reverse.  Requires pZ % 8 == 0 and cs == 1.  Same grid layout.
 __global__ void __launch_bounds__(256) gather_tiles_c1_vec8_kernel(
     const float* __restrict__ vol, int X, int Y, int Z, const int32_t* __restrict__ starts, int n_tiles, int pX,
     int pY, int pZ, FlipList flips, int n_flips, __half* __restrict__ out) {
   const int zq = pZ >> 3;
-  const size_t per_sample = (size_t)pX * pY * zq;
-  const size_t total = per_sample * n_tiles * n_flips;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    size_t n = i / per_sample;
-    size_t r = i - n * per_sample;
-    int z = (int)(r % zq) << 3;
-    int y = (int)((r / zq) % pY);
-    int x = (int)(r / ((size_t)zq * pY));
-    int t = (int)(n / n_flips);
-    int f = flips.m[n - (size_t)t * n_flips];
-    int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
-    int gx = sx + ((f & 1) ? pX - 1 - x : x);
-    int gy = sy + ((f & 2) ? pY - 1 - y : y);
-    const bool rz = (f & 4) != 0;
-    int gz = sz + (rz ? pZ - 8 - z : z);
-    const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
-    float v[8];
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(src));
-      float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(pY * zq)) return;
+  const int y = (int)(idx / (uint32_t)zq);
+  const int z = (int)(idx - (uint32_t)y * (uint32_t)zq) << 3;
+  const int x = blockIdx.y;
+  const int n = blockIdx.z;
+  const int t = n / n_flips;
+  const int f = flips.m[n - t * n_flips];
+  const int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
+  const int gx = sx + ((f & 1) ? pX - 1 - x : x);
+  const int gy = sy + ((f & 2) ? pY - 1 - y : y);
+  const bool rz = (f & 4) != 0;
+  const int gz = sz + (rz ? pZ - 8 - z : z);
+  const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
+  float v[8];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
-    }
-    __half2 h[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      h[k] = rz ? __floats2half2_rn(v[7 - 2 * k], v[6 - 2 * k]) : __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-    *reinterpret_cast<uint4*>(out + n * (size_t)pX * pY * pZ + ((size_t)x * pY + y) * pZ + z) = *reinterpret_cast<uint4*>(h);
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
   }
+  __half2 h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    h[k] = rz ? __floats2half2_rn(v[7 - 2 * k], v[6 - 2 * k]) : __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(out + ((size_t)n * pX + x) * pY * pZ + (size_t)y * pZ + z) = *reinterpret_cast<uint4*>(h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,15 +281,18 @@ template <int HC, int VZ>
 __global__ void __launch_bounds__(256) accumulate_cluster_kernel(
     const __half* __restrict__ preds_all, int ps, int heads, TileCluster tc, int pX, int pY, int pZ, FlipList flips,
     int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
+  // grid: x = chunks of 256 over (y, z quads) of one box plane, y = box plane: 32-bit index arithmetic only
   const int zq = tc.bz / VZ;
-  const size_t total = (size_t)tc.bx * tc.by * zq;
   const size_t pvox = (size_t)pX * pY * pZ;
   const size_t hstride = (size_t)X * Y * Z;
   const float nf = (float)n_flips;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gz = tc.oz + (int)(i % zq) * VZ;
-    const int gy = tc.oy + (int)((i / zq) % tc.by);
-    const int gx = tc.ox + (int)(i / ((size_t)zq * tc.by));
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(tc.by * zq)) return;
+  {
+    const int yy = (int)(idx / (uint32_t)zq);
+    const int gz = tc.oz + (int)(idx - (uint32_t)yy * (uint32_t)zq) * VZ;
+    const int gy = tc.oy + yy;
+    const int gx = tc.ox + (int)blockIdx.y;
     float* const a0 = acc + ((size_t)gx * Y + gy) * Z + gz;
     for (int h0 = 0; h0 < heads; h0 += HC) {
       float r[VZ][HC];
@@ -311,6 +316,7 @@ __global__ void __launch_bounds__(256) accumulate_cluster_kernel(
           }
         }
         const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pvox * ps + h0;
+        const uint32_t pv32 = (uint32_t)pvox;
         float s[VZ][HC];
 #pragma unroll
         for (int f = 0; f < 8; ++f) {
@@ -320,7 +326,8 @@ __global__ void __launch_bounds__(256) accumulate_cluster_kernel(
             const int fy = (m & 2) ? pY - 1 - ly : ly;
             const bool rz = (m & 4) != 0;
             const int fz = rz ? pZ - VZ - lz : lz;
-            const __half* src = preds + ((size_t)f * pvox + ((size_t)fx * pY + fy) * pZ + fz) * ps;
+            // offsets inside one tile's 8 predictions fit 32 bits (8 x 2.1 M voxels x 64 heads = 1.07 G elements)
+            const __half* src = preds + (size_t)(((uint32_t)f * pv32 + (uint32_t)((fx * pY + fy) * pZ + fz)) * (uint32_t)ps);
             if (HC * VZ <= 16 && ps == HC) {
               // the thread's VZ voxels x HC heads are contiguous: one or two 128-bit loads
               float blockv[VZ * HC];
@@ -576,16 +583,18 @@ extern "C" int fnnu_gather_tiles(const float* volume, int channels, const int vo
     FNNU_CHECK_ARG(patch[a] >= 1 && vol_dims[a] >= patch[a], "gather: volume smaller than patch on axis %d", a);
   FlipList fl;
   for (int i = 0; i < 8; ++i) fl.m[i] = i < n_flips ? (flip_masks[i] & 7) : 0;
-  size_t total = (size_t)patch[0] * patch[1] * patch[2] * n_tiles * n_flips;
+  FNNU_CHECK_ARG(patch[0] <= 65535 && n_tiles * n_flips <= 65535, "gather: grid extents");
   if (channels == 1 && c_stride == 1 && patch[2] % 8 == 0 && ((uintptr_t)out % 16) == 0) {
-    gather_tiles_c1_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+    const dim3 g8((unsigned)((patch[1] * (patch[2] / 8) + 255) / 256), (unsigned)patch[0], (unsigned)(n_tiles * n_flips));
+    gather_tiles_c1_vec8_kernel<<<g8, 256, 0, (cudaStream_t)stream>>>(
         volume, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1], patch[2], fl, n_flips,
         (__half*)out);
     FNNU_LAUNCH_CHECK();
     ++g_mem_launches;
     return FNNU_OK;
   }
-  gather_tiles_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  const dim3 gg((unsigned)((patch[1] * patch[2] + 255) / 256), (unsigned)patch[0], (unsigned)(n_tiles * n_flips));
+  gather_tiles_kernel<<<gg, 256, 0, (cudaStream_t)stream>>>(
       volume, channels, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1],
       patch[2], fl, n_flips, (__half*)out, c_stride);
   FNNU_LAUNCH_CHECK();
@@ -664,8 +673,8 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
       }
       tc.ox = lo[0]; tc.oy = lo[1]; tc.oz = lo[2];
       tc.bx = hi[0] - lo[0]; tc.by = hi[1] - lo[1]; tc.bz = hi[2] - lo[2];
-      const size_t items = (size_t)tc.bx * tc.by * (tc.bz / vz);
-      const int grid = grid_for(items, 256, 32);
+      FNNU_CHECK_ARG((size_t)8 * pvox * p_stride < ((size_t)1 << 32) && tc.bx <= 65535, "accumulate: tile too large for the 32-bit offsets");
+      const dim3 grid((unsigned)((tc.by * (tc.bz / vz) + 255) / 256), (unsigned)tc.bx);
       const __half* pr = (const __half*)preds;
       const __half* gs = (const __half*)gaussian;
       float* ac = (float*)acc;

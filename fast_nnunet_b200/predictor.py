@@ -427,7 +427,8 @@ class nnUNetPredictor(object):
         op = prog.ops[idx]
         in_d, out_d = prog.buffers[op.src][0], prog.buffers[op.dst][0]
         n = tpb * nf
-        return {'op': op.name, 'cin': op.cin, 'cout': op.cout, 'out_dims': list(out_d), 'patches_per_launch': n,
+        return {'op': op.name, 'cin': op.cin, 'cout': op.cout, 'out_dims': list(out_d), 'kernel': list(op.kernel),
+                'patches_per_launch': n,
                 'flop_per_launch': flops[idx] * n, 'ms': float(np.mean(times)), 'ms_all': [float(t) for t in times],
                 'algorithmic_bytes_per_launch': float(n * 2 * (np.prod(in_d) * op.cin + np.prod(out_d) * op.cout))}
 

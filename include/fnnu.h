@@ -115,6 +115,47 @@ int fnnu_export_labels(const void* logits, int heads, const int in_dims[3], cons
                        const int transpose_backward[3], uint8_t* labels_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pre-processing of one case (preprocessing/preprocessors/default_preprocessor.py:45-118, test-case branch)
+ * image: float32 [C][dims] in the image's own axis order; "transposed" = after transpose_forward.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* crop_to_nonzero's bounding box (cropping/cropping.py:8-39; binary_fill_holes cannot change it):
+ * bbox6_dev = {lo0, hi0, lo1, hi1, lo2, hi2} in transposed coordinates, hi exclusive; lo = INT_MAX when the image
+ * is all zeros (the caller then takes the whole image). */
+int fnnu_pre_nonzero_bbox(const float* image, int channels, const int dims[3], const int transpose_forward[3],
+                          int32_t* bbox6_dev, void* stream);
+
+/* create_nonzero_mask with binary_fill_holes (6-connectivity) on the cropped box: state[crop] = 0 non-zero voxel,
+ * 1 enclosed zero voxel (a filled hole), 2 zero voxel connected to the outside.  The reference's seg is
+ * `state == 2 ? -1 : 0`.  Synchronises the stream once per flood-fill iteration. */
+int fnnu_pre_filled_mask(const float* image, int channels, const int dims[3], const int transpose_forward[3],
+                         const int bbox_lo[3], const int crop_dims[3], uint8_t* state, int32_t* changed_dev,
+                         int max_iterations, void* stream);
+
+/* sum, sum of squares, count, min, max of one cropped channel (inside the mask when state != NULL), float64 sums;
+ * stats5_host is written after a stream synchronisation. */
+int fnnu_pre_channel_stats(const float* channel, const int dims[3], const int transpose_forward[3],
+                           const int bbox_lo[3], const int crop_dims[3], const uint8_t* state_or_null,
+                           double* stats5_host, void* stream);
+
+/* transpose + crop + intensity normalisation of one channel (default_normalization_schemes.py:27-95), float32
+ * arithmetic operation by operation as numpy performs it.  mode 0: copy (NoNormalization); 1: (clip(x, lo, hi) - a) / b
+ * (CTNormalization); 2: (x - a) / b (ZScore, RescaleTo01, RGBTo01); 3: mode 2 inside the mask only
+ * (ZScore with use_mask_for_norm).  out: float32 [crop_dims]. */
+int fnnu_pre_crop_normalize(const float* channel, const int dims[3], const int transpose_forward[3],
+                            const int bbox_lo[3], const int crop_dims[3], int mode, float a, float b, float lo,
+                            float hi, const uint8_t* state_or_null, float* out, void* stream);
+
+/* resampling_fn_data (default_resampling.py:111-192) of one channel: axis_mode[k] = 0 cubic spline (order 3), 1 nearest
+ * (the separate-z axis, order_z 0), 2 linear (order 1); clip_to_input_range = skimage.transform.resize's clip=True
+ * (per slice of the nearest axis, as the reference resizes slice by slice there).  float64 coefficients live in the
+ * caller's workspace (fnnu_pre_resample_workspace_bytes). */
+size_t fnnu_pre_resample_workspace_bytes(const int in_dims[3], const int axis_mode[3]);
+int fnnu_pre_resample_channel(const float* src, const int in_dims[3], const int out_dims[3], const int axis_mode[3],
+                              int clip_to_input_range, void* workspace, size_t workspace_bytes, float* out,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-patch network forward (replaces `self.network(x)`, :543/:555; PlainConvUNet /
  * ResidualEncoderUNet of dynamic_network_architectures as built by get_network_from_plans.py:9-43)
  * ---------------------------------------------------------------------------------------------- */

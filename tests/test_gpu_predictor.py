@@ -106,16 +106,38 @@ def test_manual_initialization_with_live_module(tmp_path):
     _compare(got, _oracle(net, x.half().float(), spec['patch'], True, None), 2)
 
 
-def test_predict_single_npy_array(tmp_path):
-    spec = nets.SMALL_PLAIN16
-    sd, net = nets.make(spec)
+@pytest.mark.parametrize('spacing', [[1.0, 1.0, 1.0], [1.6, 0.8, 0.9]])
+def test_predict_single_npy_array(tmp_path, spacing):
+    """Raw array in, label map in the image's own geometry out (predict_from_raw_data.py:423-468): device
+    pre-processing (f2) -> sliding window -> device export (f1), against the oracle's chain
+    run_case_npy -> predict_sliding_window_return_logits -> convert_predicted_logits_to_segmentation_with_correct_shape."""
+    from oracle import export as OX
+    from oracle import preprocess as OPP
+    spec, sd, net = _fixture('SMALL_PLAIN16')
     folder = _folder(tmp_path, spec, sd, normalization='CTNormalization')
-    g = np.random.default_rng(0)
-    img = g.normal(-350, 450, size=(1, 40, 36, 44)).astype(np.float32)
-    img[:, :4] = 0
+    from fast_nnunet_b200.plans import PlansManager, load_json
+    import os
+    pm = PlansManager(load_json(os.path.join(folder, 'plans.json')))
+    cm = pm.get_configuration('3d_fullres')
+    ip = pm.foreground_intensity_properties_per_channel['0']
+    # a phantom in HU-like units such that CT normalisation maps it to the range the fixture was trained on
+    x, _ = nets.phantom_volume((44, 40, 48), 1, 2, seed=9)
+    img = (x.numpy() * ip['std'] + ip['mean']).astype(np.float32)
+    img[:, :5] = 0
+    img[:, :, -4:] = 0
     p = nnUNetPredictor(device=DEV, allow_tqdm=False)
     p.initialize_from_trained_model_folder(folder, use_folds=(0,))
-    seg = p.predict_single_npy_array(img, {'spacing': [1.0, 1.0, 1.0]})
-    assert seg.shape == (40, 36, 44) and seg.dtype == np.uint8
-    with pytest.raises(NotImplementedError):
-        p.predict_single_npy_array(img, {'spacing': [2.0, 1.0, 1.0]})
+    seg = p.predict_single_npy_array(img, {'spacing': spacing})
+    assert seg.shape == img.shape[1:] and seg.dtype == np.uint8
+    data, props = OPP.run_case_npy(img.copy(), {'spacing': spacing}, list(pm.transpose_forward), cm.spacing,
+                                   cm.normalization_schemes, cm.use_mask_for_norm,
+                                   pm.foreground_intensity_properties_per_channel)
+    logits = OP.predict_sliding_window_return_logits(net.to(DEV), torch.from_numpy(data).to(DEV), spec['patch'], 0.5, True,
+                                                     (0, 1, 2)).cpu().numpy()
+    net.cpu()
+    want = OX.convert_predicted_logits_to_segmentation_with_correct_shape(logits, cm.spacing, list(pm.transpose_forward),
+                                                                          list(pm.transpose_backward), props)
+    agree = float((seg == want).mean())
+    dice = [d for d in OP.dice_per_class(seg, want, 2) if d == d]
+    print(f'predict_single_npy_array spacing {spacing}: labels agree={agree:.6f} dice={dice}')
+    assert agree >= 0.999 and min(dice) >= 0.999

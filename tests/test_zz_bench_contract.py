@@ -43,15 +43,12 @@ def test_workload_table_matches_baseline_configs():
     for name, n in expect.items():
         vol, patch = bench.WORKLOADS[name][0], bench.WORKLOADS[name][4]
         assert len(sw.tile_starts(vol[1:], patch, 0.5)) == n, name
-    dom = {'cin': 32, 'cout': 16, 'out_dims': [128, 128, 128]}
-    assert bench._conv_kernel_name(dom) == 'conv_umma_rows_kernel'
-    dom = {'cin': 64, 'cout': 32, 'out_dims': [128, 128, 128]}
-    assert bench._conv_kernel_name(dom) == 'conv_umma_kernel'
+XX
 
 
 @pytest.mark.gpu
 def test_our_arm_contract():
-    d = _run(['--workload', 'cfg1', '--steps', '1', '--warmup', '3', '--no-cpu-baseline'])
+    d = _run(['--workload', 'cfg1', '--steps', '1', '--warmup', '3', '--no-cpu-baseline', '--no-torch-gpu-baseline'])
     assert (BASE_KEYS - {'cpu_baseline'}) <= set(d), sorted(BASE_KEYS - set(d))
     assert d['n_gpus'] == 1 and d['unit'] == 'Mvoxel/s' and d['value'] > 0 and d['gpu_launches'] > 0
     for key in ('roofline', 'roofline_network', 'roofline_aggregation'):

@@ -57,3 +57,21 @@ for r in rows:
     print(f'{r[0]:3d} {r[1]:42s} {r[2]:4d}->{r[3]:<4d} {str(r[4]):18s} {r[5]:8.3f} ms {r[6]:8.1f} TFLOP/s')
 print(f'sum of ops {total:.3f} ms; whole forward {whole:.3f} ms; {tf / whole / 1e9:.1f} TFLOP/s '
       f'({tf / whole / 1e9 / 1398.2 * 100:.1f} % of 1398.2 sustained)')
+try:
+    import ctypes
+    from fast_nnunet_b200 import _lib as _L
+    lib = ctypes.CDLL(_L.LIB_PATH)
+    if hasattr(lib, 'fnnu_debug_zrows_prof'):
+        buf = (ctypes.c_longlong * 32)()
+        lib.fnnu_debug_zrows_prof(buf)
+        v = list(buf)
+        print('zrows role cycles of CTA 0, LAST zrows launch (dec5.1):')
+        print(f'  producer warp 0: wait stage-free {v[0]}, stages filled {v[1]}, total {v[2]}')
+        for m in range(2):
+            o = 8 + m * 8
+            print(f'  MMA warp {m}: wait tempty {v[o]}, wait full {v[o + 1]}, issue+commit {v[o + 2]}, steps {v[o + 3]}, total {v[o + 4]}')
+        for k in range(2):
+            o = 24 + k * 4
+            print(f'  epilogue set {k}: wait step {v[o]}, rows {v[o + 1]}, total {v[o + 2]}')
+except Exception as e:  # profiling builds only
+    print('no zrows profile:', e)
