@@ -26,6 +26,10 @@ ZROWS_W96 = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(6, 40, 96),
                  kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
 ZROWS_W72_H9 = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(4, 18, 72),
                     kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [2, 2, 2]]))
+# the network behind tests/golden/tiny_plain_unet.onnx (anisotropic first stage, 3 heads, 2 / 1 convs per stage)
+TINY_ONNX = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(16, 16, 16),
+                 kw=M.plain_arch_kwargs([8, 16, 16], [[1, 3, 3], [3, 3, 3], [3, 3, 3]], [[1, 1, 1], [1, 2, 2], [2, 2, 2]],
+                                        [2, 1, 2], [1, 2]))
 STUDENT = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
                kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
 
