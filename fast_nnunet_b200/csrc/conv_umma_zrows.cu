@@ -46,7 +46,7 @@ constexpr int kZProducerWarps = 12;
 constexpr int kZEpilogueWarp0 = 12;          // warps 12-15: plane z0, warps 16-19: plane z0 + 1
 constexpr int kZMmaWarp0 = 20;               // warps 20, 21 issue; 22, 23 only donate registers
 constexpr int kZThreads = 24 * 32;
-constexpr int kZRegsProducer = 88, kZRegsEpilogue = 88, kZRegsMma = 40;   // 384 x 88 + 256 x 88 + 128 x 40 = 768 x 80
+constexpr int kZRegsProducer = 80, kZRegsEpilogue = 96, kZRegsMma = 40;   // 384 x 80 + 256 x 96 + 128 x 40 <= 768 x 80
 constexpr int kZProw = 140;                  // positions per (plane, 8-channel group): 1 + 128 + 1, padded to 4 (mod 8)
 constexpr int kZSlots = 5;                   // y-steps resident in TMEM: 5 x 96 columns
 constexpr int kZSlotCols = 96;
@@ -60,6 +60,7 @@ struct ZCfg {
   int stage_bytes, stages, w_bytes, smem_bytes;
   int n_yseg, seg_rows;
   int issuers;
+  int prefetch_distance;   // y-steps the L2 prefetcher runs ahead of the tensor pipe (0 = off)
 };
 
 struct ZArgs {
@@ -97,6 +98,14 @@ bool plan_zrows(const ConvArgs& a, ZCfg& c) {
     issuers = (e && atoi(e) == 1) ? 1 : 2;
   }
   c.issuers = issuers;
+  static int pf = -1;
+  if (pf < 0) {
+    const char* e = getenv("FNNU_ZROWS_PREFETCH");
+    pf = e ? atoi(e) : 8;
+    if (pf < 0) pf = 0;
+    if (pf > kZStepBars - 2) pf = kZStepBars - 2;
+  }
+  c.prefetch_distance = pf;
   return true;
 }
 
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
   uint64_t* w_bar = tempty_bar + kZSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                                      // [16]
+  volatile int* progress = reinterpret_cast<volatile int*>(bias_s + 16);                        // [2] y-steps issued per issuer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 16) bias_s[threadIdx.x] = (a.bias && (int)threadIdx.x < a.cout) ? a.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 2) progress[threadIdx.x] = 0;
   // halo positions (and everything else) start as zeros; producers only ever write in-image positions
   {
     uint4* r4 = reinterpret_cast<uint4*>(ring);
@@ -398,6 +409,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
               if (pl0) z_issue_plane<CHUNKS, 0, 96, 0>(d, da_st, b_desc0, idesc48, accum);  // z0-1 -> tile 0
               if (pl3) z_issue_plane<CHUNKS, 3, 0, 0>(d + 48, da_st, b_desc0, idesc48, accum);   // z0+2 -> tile 1
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+              progress[me] = t + c.issuers;  // this issuer's next step (steps are dealt round-robin to the issuers)
             }
             __syncwarp();
             ZPROF_ADD(2, clock64() - w2);
@@ -415,6 +427,37 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         o[0] = zp[0]; o[1] = zp[1]; o[2] = zp[2]; o[3] = zp[3]; o[4] = clock64() - zt0;
       }
 #endif
+    } else if (me == 2 && c.prefetch_distance > 0) {
+      // =========================== L2 PREFETCHER (a warp that would otherwise only donate registers) ===============
+      // The producers are bound by the latency of their loads (the previous layer's output comes from HBM: 4.3 GB per
+      // launch against 126 MB of L2).  One bulk prefetch per (plane, row), issued `prefetch_distance` y-steps ahead of
+      // the tensor pipe, turns those loads into L2 hits.
+      const size_t row_bytes = (size_t)c.W * a.src_cs * 2;
+      const size_t zplane_bytes = (size_t)c.H * row_bytes;
+      const uint32_t pf_bytes = (uint32_t)((size_t)c.W * a.cin * 2) & ~15u;
+      const int dist = c.prefetch_distance;
+      int t = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        int b, z0, ya, yb;
+        decode(u, b, z0, ya, yb);
+        const int n_rows = (yb - ya) + 2;
+        const int zi = z0 - 1 + lane;                       // lanes 0-3: planes z0-1 .. z0+2
+        const bool pl_ok = lane < 4 && zi >= 0 && zi < c.D;
+        const char* plane = reinterpret_cast<const char*>(a.src) + ((size_t)b * c.D + zi) * zplane_bytes;
+        for (int j = 0; j < n_rows; ++j, ++t) {
+          // pace on the issuers' progress counters (plain shared-memory words: no barrier phase to miss, and the
+          // counters reach their final value whatever happens to this warp)
+          while (true) {
+            int done = progress[0];
+            if (c.issuers == 2) done = min(done, (int)progress[1]);
+            if (done + dist >= t) break;
+            __nanosleep(256);
+          }
+          const int y_in = ya - 1 + j;
+          if (pl_ok && y_in >= 0 && y_in < c.H)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(plane + (size_t)y_in * row_bytes), "r"(pf_bytes) : "memory");
+        }
+      }
     }
   } else {
     // =========================== EPILOGUE (set k = output plane z0 + k) ===========================
@@ -425,6 +468,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(k * 48);
     const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && a.cout == 16;
     const bool col_ok = x < c.W;
+    const bool has_bias = a.bias != nullptr;
     const size_t out_row_stride = (size_t)c.W * a.dst_cs;
     float s1[16], s2[16];
 #pragma unroll
@@ -476,38 +520,40 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         if (slot_b == kZSlots) slot_b = 0;
         int slot_c = slot_b + 1;
         if (slot_c == kZSlots) slot_c = 0;
-        // two batches of 8 channels (24 live TMEM registers instead of 48: the producers get the difference)
-#pragma unroll
-        for (int g0 = 0; g0 < 16; g0 += 8) {
-          uint32_t r0[8], r1[8], r2[8];
-          tmem_ld8_nowait(t_lane + (uint32_t)(slot_a * kZSlotCols + 0 + g0), r0);     // T[y-1], ky = 0
-          tmem_ld8_nowait(t_lane + (uint32_t)(slot_b * kZSlotCols + 16 + g0), r1);    // T[y],   ky = 1
-          tmem_ld8_nowait(t_lane + (uint32_t)(slot_c * kZSlotCols + 32 + g0), r2);    // T[y+1], ky = 2
+        // one TMEM round per row: the three 16-column groups are in flight together
+        {
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_a * kZSlotCols + 0), r0);     // T[y-1], ky = 0
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_b * kZSlotCols + 16), r1);    // T[y],   ky = 1
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_c * kZSlotCols + 32), r2);    // T[y+1], ky = 2
           tmem_wait_ld();
-          if (g0 == 8) {
-            // the tile of step t is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
-            tc_fence_before();
-            mbar_arrive_warp(&tempty_bar[slot_a]);
-          }
+          // the tile of step t is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
+          tc_fence_before();
+          mbar_arrive_warp(&tempty_bar[slot_a]);
           if (col_ok) {
-            __half2 hv[4];
+            __half2 hv[8];
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float2 bj = *reinterpret_cast<const float2*>(bias_s + g0 + j);
-              const float v0 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]) + bj.x;
-              const float v1 = (__uint_as_float(r0[j + 1]) + __uint_as_float(r1[j + 1])) + __uint_as_float(r2[j + 1]) + bj.y;
-              s1[g0 + j] += v0;
-              s2[g0 + j] = fmaf(v0, v0, s2[g0 + j]);
-              s1[g0 + j + 1] += v1;
-              s2[g0 + j + 1] = fmaf(v1, v1, s2[g0 + j + 1]);
+            for (int j = 0; j < 16; j += 2) {
+              float v0 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+              float v1 = (__uint_as_float(r0[j + 1]) + __uint_as_float(r1[j + 1])) + __uint_as_float(r2[j + 1]);
+              if (has_bias) {       // only a convolution WITHOUT a following InstanceNorm keeps its bias (program.py)
+                const float2 bj = *reinterpret_cast<const float2*>(bias_s + j);
+                v0 += bj.x;
+                v1 += bj.y;
+              }
+              s1[j] += v0;
+              s2[j] = fmaf(v0, v0, s2[j]);
+              s1[j + 1] += v1;
+              s2[j + 1] = fmaf(v1, v1, s2[j + 1]);
               hv[j >> 1] = __floats2half2_rn(v0, v1);
             }
             if (vec_store) {
-              reinterpret_cast<uint4*>(out_px)[g0 >> 3] = *reinterpret_cast<uint4*>(&hv[0]);
+              reinterpret_cast<uint4*>(out_px)[0] = *reinterpret_cast<uint4*>(&hv[0]);
+              reinterpret_cast<uint4*>(out_px)[1] = *reinterpret_cast<uint4*>(&hv[4]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (g0 + j < a.cout) out_px[g0 + j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
+              for (int j = 0; j < 16; ++j)
+                if (j < a.cout) out_px[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
         }

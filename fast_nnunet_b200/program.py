@@ -10,7 +10,8 @@ Fusion decisions encoded here:
     pending transform applied by whichever operator loads the buffer next;
   * `torch.cat((up, skip), 1)` is never executed: the transposed conv writes channels [0, C) and the
     encoder stage's last conv writes channels [C, 2C) of one pre-allocated buffer;
-  * only the highest-resolution seg layer is evaluated (deep supervision off at inference).
+  * only the highest-resolution seg layer is evaluated (deep supervision off at inference);
+  * the bias of a convolution that feeds an InstanceNorm is dropped (IN(x + b) = IN(x)).
 """
 from __future__ import annotations
 
@@ -159,7 +160,10 @@ class _Builder:
 
     def conv_norm(self, prefix, src, src_coff, cin, cout, kernel, stride, dst, dst_coff, slope, bias=None, name=''):
         """ConvDropoutNormReLU under `prefix` ('....convs.0' etc.): keys conv.weight, conv.bias, norm.*"""
-        use_bias = self.conv_bias if bias is None else bias
+        # A bias in front of InstanceNorm is a mathematical no-op (IN(x + b) = IN(x): the mean absorbs it, the variance
+        # does not see it), so it is not lowered: one add per output less in every epilogue, and the fp16 raw
+        # activations keep their precision when |b| is large against the channel's spread.
+        use_bias = False
         w = self.get(prefix + '.conv.weight')
         assert w.shape == (cout, cin, *kernel), f'{prefix}: weight {w.shape} != {(cout, cin, *kernel)}'
         self.p.ops.append(Op(op=_lib.OP_CONV, src=src, src_coff=src_coff, dst=dst, dst_coff=dst_coff, cin=cin,

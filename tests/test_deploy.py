@@ -114,8 +114,7 @@ def test_predictor_from_deployment_matches_oracle(tmp_path):
     pred = deploy.predictor_from_deployment(str(tmp_path / 'model.ini'), device=dev)
     assert pred.use_mirroring is False and pred.label_manager.num_segmentation_heads == 3
     g = np.random.default_rng(0)
-    img = g.normal(400, 500, size=(1, 20, 36, 40)).astype(np.float32)
-    img[:, :2] = 0
+    img = g.normal(400, 500, size=(1, 20, 36, 40)).astype(np.float32)       # no zero border: nothing is cropped
     spacing = [2.0, 0.9765625, 0.9765625]
     seg = pred.predict_single_npy_array(img, {'spacing': spacing})
     cfg = deploy.read_engine_ini(str(tmp_path / 'model.ini'))
@@ -125,7 +124,7 @@ def test_predictor_from_deployment_matches_oracle(tmp_path):
                                                       True, None).cpu().numpy()
     want = OX.convert_predicted_logits_to_segmentation_with_correct_shape(logits, cfg['target_spacing'], [0, 1, 2],
                                                                           [0, 1, 2], props)
-    assert seg.shape == img.shape[1:]
+    assert seg.shape == img.shape[1:] == tuple(logits.shape[1:])
     # random-init weights: near-tied logits, so the bar is on the logits' consequence only where the margin is real
     lg = torch.from_numpy(logits.astype(np.float32))
     top2 = torch.topk(lg, 2, dim=0).values

@@ -74,7 +74,8 @@ def test_intermediate_buffers_and_stats():
     raw = eng.buffer_tensor(op0.dst, 2)[..., op0.dst_coff:op0.dst_coff + op0.cout].float().cpu()
     conv = net.encoder.stages[0][0].convs[0].conv
     with torch.no_grad():
-        want = conv(x.half().float()).permute(0, 2, 3, 4, 1)
+        # the engine does not lower a bias that feeds an InstanceNorm (program.py: IN(x + b) = IN(x))
+        want = torch.nn.functional.conv3d(x.half().float(), conv.weight, None, conv.stride, conv.padding).permute(0, 2, 3, 4, 1)
     assert (raw - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
     st = eng.stats_tensor(op0.dst, 2)[:, op0.dst_coff:op0.dst_coff + op0.cout].cpu()
     s1 = raw.double().sum(dim=(1, 2, 3))
