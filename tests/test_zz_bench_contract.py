@@ -43,7 +43,14 @@ def test_workload_table_matches_baseline_configs():
     for name, n in expect.items():
         vol, patch = bench.WORKLOADS[name][0], bench.WORKLOADS[name][4]
         assert len(sw.tile_starts(vol[1:], patch, 0.5)) == n, name
-XX
+    dom = {'cin': 32, 'cout': 16, 'out_dims': [128, 128, 128], 'kernel': [3, 3, 3]}
+    assert bench._conv_kernel_name(dom) == 'conv_umma_zrows_kernel'       # z-pair row streaming: Cout <= 16, 3x3x3
+    dom = {'cin': 32, 'cout': 32, 'out_dims': [64, 64, 64], 'kernel': [3, 3, 3]}
+    assert bench._conv_kernel_name(dom) == 'conv_umma_rows_kernel'
+    dom = {'cin': 16, 'cout': 16, 'out_dims': [160, 96, 96], 'kernel': [1, 3, 3]}
+    assert bench._conv_kernel_name(dom) == 'conv_umma_rows_kernel'
+    dom = {'cin': 64, 'cout': 32, 'out_dims': [64, 64, 64], 'kernel': [3, 3, 3]}
+    assert bench._conv_kernel_name(dom) == 'conv_umma_kernel'
 
 
 @pytest.mark.gpu
