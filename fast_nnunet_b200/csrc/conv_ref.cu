@@ -466,16 +466,116 @@ __global__ void __launch_bounds__(256) conv_pointwise_head_kernel(ConvArgs a) {
   }
 }
 
+// Segmentation head with many classes (9 .. 64 per pass, e.g. the 61 labels of bone_turbo): HBM-bound (32 bytes in,
+// 2 x heads bytes out per voxel), 2 x Cin x heads FLOP per voxel on the CUDA cores.  One thread per voxel keeps 64
+// fp32 accumulators in registers; the weights sit in shared memory as [cin][64] so that one LDS.128 broadcast feeds four
+// FMAs; the padded head vector of a voxel leaves as 16-byte stores.  Heads beyond 64 take further passes.
+__global__ void __launch_bounds__(128) conv_pointwise_head_wide_kernel(ConvArgs a) {
+  extern __shared__ float smem[];
+  float* w_s = smem;                  // [cin][64] of the current pass
+  float* xs = w_s + 64 * a.cin;       // scale, shift, slope [cin]
+  float* xh = xs + a.cin;
+  float* xl = xh + a.cin;
+  float* b_s = xl + a.cin;            // [64] bias of the current pass
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < a.cin; c += 128) {
+    float sc, sh;
+    const ChanMeta m = a.src_meta[c];
+    xform_from_stats(a.src_stats + ((size_t)b * a.src_stat_stride + c) * 2, m, a.src_inv_count, sc, sh);
+    xs[c] = sc;
+    xh[c] = sh;
+    xl[c] = m.eps < 0.f ? 1.f : m.slope;
+  }
+  const size_t nv = (size_t)a.in_d[0] * a.in_d[1] * a.in_d[2];
+  const __half* src_b = a.src + (size_t)b * nv * a.src_cs;
+  __half* dst_b = a.dst + (size_t)b * nv * a.dst_cs;
+  for (int co0 = 0; co0 < a.cout; co0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * a.cin; i += 128) {
+      const int ci = i >> 6, co = co0 + (i & 63);
+      w_s[i] = co < a.cout ? __ldg(a.w + (size_t)ci * a.cout_pad + co) : 0.f;       // packed [tap = 0][cin][cout_pad]
+    }
+    if (threadIdx.x < 64) b_s[threadIdx.x] = (a.bias && co0 + (int)threadIdx.x < a.cout) ? __ldg(a.bias + co0 + threadIdx.x) : 0.f;
+    __syncthreads();
+    // the store is vectorised when the destination row of a voxel holds the 64 (padded) heads of this pass
+    const bool vec_out = a.dst_cs % 8 == 0 && co0 + 64 <= a.dst_cs && ((uintptr_t)a.dst % 16) == 0;
+    for (size_t v = (size_t)blockIdx.x * 128 + threadIdx.x; v < nv; v += (size_t)gridDim.x * 128) {
+      float acc[64];
+#pragma unroll
+      for (int o4 = 0; o4 < 16; ++o4) {
+        const float4 b4 = reinterpret_cast<const float4*>(b_s)[o4];
+        acc[4 * o4] = b4.x; acc[4 * o4 + 1] = b4.y; acc[4 * o4 + 2] = b4.z; acc[4 * o4 + 3] = b4.w;
+      }
+      const uint4* p = reinterpret_cast<const uint4*>(src_b + v * a.src_cs);
+      for (int c8 = 0; c8 < a.cin; c8 += 8) {
+        const uint4 raw = __ldg(p + (c8 >> 3));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 f = __half22float2(h2[e >> 1]);
+          const int c = c8 + e;
+          float x = fmaf((e & 1) ? f.y : f.x, xs[c], xh[c]);
+          x = fmaxf(x, x * xl[c]);
+          x = __half2float(__float2half_rn(x));      // every back end feeds fp16-rounded activations to its conv
+          const float4* wr = reinterpret_cast<const float4*>(w_s + c * 64);
+#pragma unroll
+          for (int o4 = 0; o4 < 16; ++o4) {
+            const float4 w4 = wr[o4];
+            acc[4 * o4 + 0] = fmaf(x, w4.x, acc[4 * o4 + 0]);
+            acc[4 * o4 + 1] = fmaf(x, w4.y, acc[4 * o4 + 1]);
+            acc[4 * o4 + 2] = fmaf(x, w4.z, acc[4 * o4 + 2]);
+            acc[4 * o4 + 3] = fmaf(x, w4.w, acc[4 * o4 + 3]);
+          }
+        }
+      }
+      __half* q = dst_b + v * a.dst_cs + co0;
+      if (vec_out) {
+#pragma unroll
+        for (int o8 = 0; o8 < 8; ++o8) {
+          __half2 h[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int o = 8 * o8 + 2 * k;
+            h[k] = __floats2half2_rn(acc[o], acc[o + 1]);
+          }
+          reinterpret_cast<uint4*>(q)[o8] = *reinterpret_cast<uint4*>(h);
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < 64; ++o)
+          if (co0 + o < a.cout) q[o] = __float2half_rn(acc[o]);
+      }
+    }
+  }
+}
+
+static bool pointwise_head_wide_ok(const ConvArgs& a) {
+  if (a.transposed || a.dst_stats) return false;
+  if (a.k[0] != 1 || a.k[1] != 1 || a.k[2] != 1 || a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
+  return a.cout > 8 && a.cin % 8 == 0 && a.cin <= 64 && a.src_cs % 8 == 0 && ((uintptr_t)a.src % 16) == 0;
+}
+
 static bool pointwise_head_ok(const ConvArgs& a) {
   if (a.transposed || a.dst_stats) return false;
   if (a.k[0] != 1 || a.k[1] != 1 || a.k[2] != 1 || a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
   return a.cout <= 8 && a.cin % 8 == 0 && a.cin <= 1024 && a.src_cs % 8 == 0 && ((uintptr_t)a.src % 16) == 0;
 }
 
-bool direct_specialised(const ConvArgs& a) { return small_cin_ok(a) || pointwise_head_ok(a); }
-bool prefer_cuda_cores(const ConvArgs& a) { return pointwise_head_ok(a); }
+bool direct_specialised(const ConvArgs& a) { return small_cin_ok(a) || pointwise_head_ok(a) || pointwise_head_wide_ok(a); }
+bool prefer_cuda_cores(const ConvArgs& a) { return pointwise_head_ok(a) || pointwise_head_wide_ok(a); }
 
 int launch_conv_specialised(const ConvArgs& a, cudaStream_t s) {
+  if (pointwise_head_wide_ok(a)) {
+    const size_t nv = (size_t)a.in_d[0] * a.in_d[1] * a.in_d[2];
+    int blocks = (int)((nv + 127) / 128);
+    const int cap = num_sms() * 16 / (a.batch > 8 ? 8 : a.batch) + 1;
+    if (blocks > cap) blocks = cap;
+    const dim3 grid((unsigned)blocks, (unsigned)a.batch);
+    const size_t smem = (size_t)(64 * a.cin + 3 * a.cin + 64) * sizeof(float);
+    conv_pointwise_head_wide_kernel<<<grid, 128, smem, s>>>(a);
+    FNNU_LAUNCH_CHECK();
+    return FNNU_OK;
+  }
   if (pointwise_head_ok(a)) {
     const size_t nv = (size_t)a.in_d[0] * a.in_d[1] * a.in_d[2];
     int blocks = (int)((nv + 255) / 256);

@@ -21,6 +21,15 @@
 //    rounding error scales with the normalised value and not with mean * scale.
 //  * eight epilogue warps (one set of four per output plane) drain the tiles: out[y] = T[y-1][ky 0] + T[y][ky 1] +
 //    T[y+1][ky 2], the same-lane sum of conv_umma_rows.cu.
+//
+// Shapes (template <CHUNKS = Cin / 16, CP = padded Cout, ZC = output planes per pass, NKZ = kernel extent along z>):
+//   <1|2, 16, 2, 3>  the z-pair form described above (even depth)
+//   <1|2, 16, 1, 1|3>, <1|2, 32, 1, 1|3>  one output plane per pass: 1x3x3 kernels (anisotropic first stages), odd depths
+//                    and Cout = 32 (two tiles of 96 columns do not leave room for five y-steps in TMEM); with Cout = 32
+//                    the two epilogue warp sets split the channels instead of the planes.
+// A y-step's shared-memory stage holds NPL = ZC + NKZ - 1 input planes; input plane pl feeds output tiles
+// zt in [max(0, pl - NKZ + 1), min(ZC - 1, pl)] with kz = pl - zt, one MMA per (kx, 16 input channels) whose N spans those
+// tiles: weights are packed [kx][chunk][half][n = (NKZ - 1 - kz) * 3 CP + ky * CP + co][8].
 #include "common.cuh"
 #include "ops.cuh"
 #include "umma_ptx.cuh"
@@ -48,15 +57,14 @@ constexpr int kZMmaWarp0 = 20;               // warps 20, 21 issue; 22, 23 only 
 constexpr int kZThreads = 24 * 32;
 constexpr int kZRegsProducer = 80, kZRegsEpilogue = 96, kZRegsMma = 40;   // 384 x 80 + 256 x 96 + 128 x 40 <= 768 x 80
 constexpr int kZProw = 140;                  // positions per (plane, 8-channel group): 1 + 128 + 1, padded to 4 (mod 8)
-constexpr int kZSlots = 5;                   // y-steps resident in TMEM: 5 x 96 columns
-constexpr int kZSlotCols = 96;
+constexpr int kZMaxSlots = 8;                // y-steps resident in TMEM: 512 / (ZC * 3 * CP) columns, at most 8
 constexpr int kZStepBars = 16;               // ring of "y-step done" barriers (> stages, > slots)
 constexpr int kZMaxStages = 12;
 constexpr int kZSmemLimit = 227 * 1024;
 
 struct ZCfg {
   int D, H, W;
-  int chunks;
+  int chunks, cp, zc, nkz, npl;
   int stage_bytes, stages, w_bytes, smem_bytes;
   int n_yseg, seg_rows;
   int issuers;
@@ -73,15 +81,19 @@ bool plan_zrows(const ConvArgs& a, ZCfg& c) {
   memset(&c, 0, sizeof(c));
   if (a.transposed) return false;
   if (a.s[0] != 1 || a.s[1] != 1 || a.s[2] != 1) return false;
-  if (a.k[0] != 3 || a.k[1] != 3 || a.k[2] != 3) return false;
+  if ((a.k[0] != 3 && a.k[0] != 1) || a.k[1] != 3 || a.k[2] != 3) return false;
   if (a.cin != 16 && a.cin != 32) return false;
-  if (a.cout_pad != 16) return false;
+  if (a.cout_pad != 16 && a.cout_pad != 32) return false;
   if (a.src_cs % 8 != 0 || ((uintptr_t)a.src % 16) != 0) return false;
   c.D = a.in_d[0]; c.H = a.in_d[1]; c.W = a.in_d[2];
-  if (c.W > 128 || c.W < 64 || (c.D & 1) || c.H < 8) return false;
+  if (c.W > 128 || c.W < 64 || c.H < 8) return false;
   c.chunks = a.cin / 16;
-  c.stage_bytes = 4 * 2 * c.chunks * kZProw * 16;
-  c.w_bytes = 3 * c.chunks * 2 * 144 * 16;
+  c.cp = a.cout_pad;
+  c.nkz = a.k[0];
+  c.zc = (c.cp == 16 && c.nkz == 3 && !(c.D & 1)) ? 2 : 1;
+  c.npl = c.zc + c.nkz - 1;
+  c.stage_bytes = c.npl * 2 * c.chunks * kZProw * 16;
+  c.w_bytes = 3 * c.chunks * 2 * (c.nkz * 3 * c.cp) * 16;
   const int misc = 2048;
   int st = (kZSmemLimit - misc - c.w_bytes) / c.stage_bytes;
   if (st > kZMaxStages) st = kZMaxStages;
@@ -90,7 +102,7 @@ bool plan_zrows(const ConvArgs& a, ZCfg& c) {
   c.stages = st;
   c.smem_bytes = c.w_bytes + c.stages * c.stage_bytes + misc;
   c.n_yseg = 1;
-  while ((long long)a.batch * (c.D / 2) * c.n_yseg < 3LL * num_sms() && c.H / (c.n_yseg * 2) >= 8) c.n_yseg *= 2;
+  while ((long long)a.batch * (c.D / c.zc) * c.n_yseg < 3LL * num_sms() && c.H / (c.n_yseg * 2) >= 8) c.n_yseg *= 2;
   c.seg_rows = (c.H + c.n_yseg - 1) / c.n_yseg;
   static int issuers = 0;
   if (!issuers) {
@@ -109,16 +121,48 @@ bool plan_zrows(const ConvArgs& a, ZCfg& c) {
   return true;
 }
 
+// Geometry of one (CP, ZC, NKZ) instantiation, all compile-time.
+template <int CP, int ZC, int NKZ>
+struct ZGeo {
+  static constexpr int TILE_N = 3 * CP;                 // one output plane's accumulator tile: (ky, co)
+  static constexpr int SLOT_COLS = ZC * TILE_N;         // a y-step's TMEM columns
+  static constexpr int SLOTS = (512 / SLOT_COLS) < kZMaxSlots ? (512 / SLOT_COLS) : kZMaxSlots;
+  static constexpr int NPL = ZC + NKZ - 1;              // input planes per stage
+  static constexpr int PZ = (NKZ - 1) / 2;              // plane PZ is output plane z0 itself: always inside the volume
+  static constexpr int BN = NKZ * TILE_N;               // N extent of the packed weights
+  static constexpr int zt_lo(int pl) { return pl - NKZ + 1 > 0 ? pl - NKZ + 1 : 0; }
+  static constexpr int zt_hi(int pl) { return pl < ZC - 1 ? pl : ZC - 1; }
+  static constexpr int n_of(int pl) { return (zt_hi(pl) - zt_lo(pl) + 1) * TILE_N; }
+  static constexpr int d_off(int pl) { return zt_lo(pl) * TILE_N; }
+  static constexpr int b_col(int pl) { return (NKZ - 1 - (pl - zt_lo(pl))) * TILE_N; }
+};
+
 // MMAs of one input plane: 3 kx x CHUNKS, descriptor offsets (16-byte units) are template constants.
-template <int CHUNKS, int PL, int NCOL0, int I>
+template <int CHUNKS, int PL, int BN, int NCOL0, int I>
 __device__ __forceinline__ void z_issue_plane(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t& accum) {
   if constexpr (I < 3 * CHUNKS) {
     constexpr int kx = I / CHUNKS, kc = I % CHUNKS;
     constexpr uint32_t a_off = (uint32_t)((PL * 2 * CHUNKS + kc * 2) * kZProw + kx);
-    constexpr uint32_t b_off = (uint32_t)(((kx * CHUNKS + kc) * 2) * 144 + NCOL0);
+    constexpr uint32_t b_off = (uint32_t)(((kx * CHUNKS + kc) * 2) * BN + NCOL0);
     umma_f16_off<a_off, b_off>(d, da, db, idesc, accum);
     accum = 1;
-    z_issue_plane<CHUNKS, PL, NCOL0, I + 1>(d, da, db, idesc, accum);
+    z_issue_plane<CHUNKS, PL, BN, NCOL0, I + 1>(d, da, db, idesc, accum);
+  }
+}
+
+// every plane of a y-step except the first-touch plane PZ: first (FULL = true) the planes whose MMAs span the whole
+// slot, then the edge planes — MMAs of equal N back to back (the order 96, 48, 96, 48 measured 20 % slower on the
+// Cin = 32 layer than 96, 96, 48, 48)
+template <int CHUNKS, int CP, int ZC, int NKZ, int PL, bool FULL>
+__device__ __forceinline__ void z_issue_other_planes(uint32_t d, uint64_t da, uint64_t db, uint32_t pl_ok, uint32_t& accum) {
+  using G = ZGeo<CP, ZC, NKZ>;
+  if constexpr (PL < G::NPL) {
+    if constexpr (PL != G::PZ && (G::n_of(PL) == G::SLOT_COLS) == FULL) {
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(G::n_of(PL) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      if ((pl_ok >> PL) & 1)
+        z_issue_plane<CHUNKS, PL, G::BN, G::b_col(PL), 0>(d + (uint32_t)G::d_off(PL), da, db, idesc, accum);
+    }
+    z_issue_other_planes<CHUNKS, CP, ZC, NKZ, PL + 1, FULL>(d, da, db, pl_ok, accum);
   }
 }
 
@@ -145,8 +189,13 @@ __device__ __forceinline__ uint4 zxform8(const uint4 raw, const __half2* m2, con
   return o;
 }
 
-template <int CHUNKS>
+template <int CHUNKS, int CP, int ZC, int NKZ>
 __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __grid_constant__ ZArgs p) {
+  using G = ZGeo<CP, ZC, NKZ>;
+  constexpr int kZSlots = G::SLOTS;
+  constexpr int kZSlotCols = G::SLOT_COLS;
+  // epilogue warp sets that have work: one per output plane (ZC = 2) or one per half of 32 output channels (CP = 32)
+  constexpr int kSets = (ZC == 2 || CP == 32) ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const ZCfg& c = p.c;
   const ConvArgs& a = p.a;
@@ -154,11 +203,11 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
   uint8_t* ring = smem + c.w_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)c.stages * c.stage_bytes);   // [kZMaxStages]
   uint64_t* step_bar = full_bar + kZMaxStages;                                                  // [kZStepBars]
-  uint64_t* tempty_bar = step_bar + kZStepBars;                                                 // [kZSlots]
-  uint64_t* w_bar = tempty_bar + kZSlots;
+  uint64_t* tempty_bar = step_bar + kZStepBars;                                                 // [kZMaxSlots]
+  uint64_t* w_bar = tempty_bar + kZMaxSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                                      // [16]
-  volatile int* progress = reinterpret_cast<volatile int*>(bias_s + 16);                        // [2] y-steps issued per issuer
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);                                      // [32]
+  volatile int* progress = reinterpret_cast<volatile int*>(bias_s + 32);                        // [2] y-steps issued per issuer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,11 +217,11 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) mbar_init(&full_bar[s], kGroupWarps);
     for (int s = 0; s < kZStepBars; ++s) mbar_init(&step_bar[s], 1);
-    for (int s = 0; s < kZSlots; ++s) mbar_init(&tempty_bar[s], 8);
+    for (int s = 0; s < kZSlots; ++s) mbar_init(&tempty_bar[s], 4 * kSets);       // one arrival per epilogue warp
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 16) bias_s[threadIdx.x] = (a.bias && (int)threadIdx.x < a.cout) ? a.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = (a.bias && (int)threadIdx.x < a.cout) ? a.bias[threadIdx.x] : 0.f;
   if (threadIdx.x < 2) progress[threadIdx.x] = 0;
   // halo positions (and everything else) start as zeros; producers only ever write in-image positions
   {
@@ -195,17 +244,28 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     bulk_g2s(w_s, a.w_umma, (uint32_t)c.w_bytes, w_bar);
   }
 
-  // unit u -> (sample b, z pair zp, y segment): output planes 2 zp, 2 zp + 1, rows [ya, yb)
-  const int n_zp = c.D >> 1;
+  // unit u -> (sample b, z chunk zp, y segment): output planes ZC zp .. ZC zp + ZC - 1, rows [ya, yb)
+  const int n_zp = c.D / ZC;
   auto decode = [&](int u, int& b, int& z0, int& ya, int& yb) {
     const int zp = u % n_zp;
     u /= n_zp;
     const int seg = u % c.n_yseg;
     b = u / c.n_yseg;
-    z0 = 2 * zp;
+    z0 = ZC * zp;
     ya = seg * c.seg_rows;
     yb = ya + c.seg_rows;
     if (yb > c.H) yb = c.H;
+  };
+
+  // bit pl: input plane z0 - PZ + pl lies inside the volume (the others are skipped by producers and issuers alike)
+  auto planes_ok = [&](int z0) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int pl = 0; pl < G::NPL; ++pl) {
+      const int zi = z0 - G::PZ + pl;
+      if (zi >= 0 && zi < c.D) m |= 1u << pl;
+    }
+    return m;
   };
 
   if (warp < kZProducerWarps) {
@@ -228,8 +288,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     const uint32_t gstep = (uint32_t)(32 * a.src_cs) * 2u;
     const uint32_t plane_bytes = (uint32_t)(2 * CHUNKS * kZProw) * 16u;
     const uint32_t my_off = (uint32_t)(q * kZProw + x0 + 1) * 16u;      // + it * 512
-    const size_t row_bytes = (size_t)c.W * a.src_cs * 2;
-    const size_t zplane_bytes = (size_t)c.H * row_bytes;
+    // one 64-bit base per unit; everything below it is 32-bit offsets (a plane of 128 x 128 x 32 fp16 is 1 MB)
+    const uint32_t row_bytes = (uint32_t)(c.W * a.src_cs * 2);
+    const uint32_t zplane_bytes = (uint32_t)c.H * row_bytes;
     const uint32_t ring_u32 = smem_u32(ring);
     const bool full_w = c.W == 128;                          // every lane's four positions lie inside the row
     int t = 0, t_grp = 0, stage = 0;                         // step counter, its group, its stage
@@ -272,9 +333,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         cur_b = b;
       }
       const int n_rows = (yb - ya) + 2;
-      // planes z0-1 .. z0+2; out-of-volume planes are skipped here and by the MMA warps
-      const uint32_t pl_ok = (z0 >= 1 ? 1u : 0u) | 2u | 4u | (z0 + 2 < c.D ? 8u : 0u);
-      const char* vol0 = reinterpret_cast<const char*>(a.src) + ((size_t)b * c.D + (z0 - 1)) * zplane_bytes;
+      // planes z0 - PZ .. z0 - PZ + NPL - 1; out-of-volume planes are skipped here and by the MMA warps
+      const uint32_t pl_ok = planes_ok(z0);
+      const char* vol0 = reinterpret_cast<const char*>(a.src) + ((long long)b * c.D + (z0 - G::PZ)) * (long long)zplane_bytes + goff0;
       for (int j = 0; j < n_rows; ++j) {
         const bool mine = t_grp == grp;
         const int my_stage = stage;
@@ -299,37 +360,38 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
           // a row outside the image: zeros (the conv's zero padding applies to the NORMALISED activations)
           wait_stage_free();
 #pragma unroll
-          for (int pl = 0; pl < 4; ++pl)
+          for (int pl = 0; pl < G::NPL; ++pl)
             if ((pl_ok >> pl) & 1) {
 #pragma unroll
               for (int it = 0; it < 4; ++it)
                 if ((in_w >> it) & 1) sts16(st + pl * plane_bytes + it * 512, make_uint4(0, 0, 0, 0));
             }
         } else {
-          const char* row0 = vol0 + (size_t)y_in * row_bytes + goff0;
+          const uint32_t row_off = (uint32_t)y_in * row_bytes;
+          // unrolled on purpose: with `#pragma unroll 1` enc0.1 went from 1.40 to 1.83 ms per 32 patches
 #pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
+          for (int hp = 0; hp < (G::NPL + 1) / 2; ++hp) {
             // two planes per round: 8 independent 16-byte loads in flight per thread; plane validity is CTA-uniform
-            const bool va = (pl_ok >> (2 * hp)) & 1, vb = (pl_ok >> (2 * hp + 1)) & 1;
-            const char* pa = row0 + (size_t)(2 * hp) * zplane_bytes;
-            const char* pb = pa + zplane_bytes;
+            const bool va = (pl_ok >> (2 * hp)) & 1, vb = (2 * hp + 1 < G::NPL) && ((pl_ok >> (2 * hp + 1)) & 1);
+            const uint32_t oa = row_off + (uint32_t)(2 * hp) * zplane_bytes;
+            const uint32_t ob = oa + zplane_bytes;
             uint4 v[8];
             if (full_w) {
               if (va) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) v[it] = ldg_nc16(pa + it * gstep);
+                for (int it = 0; it < 4; ++it) v[it] = ldg_nc16(vol0 + (oa + it * gstep));
               }
               if (vb) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) v[4 + it] = ldg_nc16(pb + it * gstep);
+                for (int it = 0; it < 4; ++it) v[4 + it] = ldg_nc16(vol0 + (ob + it * gstep));
               }
             } else {
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 v[it] = make_uint4(0, 0, 0, 0);
                 v[4 + it] = make_uint4(0, 0, 0, 0);
-                if (va && ((in_w >> it) & 1)) v[it] = ldg_nc16(pa + it * gstep);
-                if (vb && ((in_w >> it) & 1)) v[4 + it] = ldg_nc16(pb + it * gstep);
+                if (va && ((in_w >> it) & 1)) v[it] = ldg_nc16(vol0 + (oa + it * gstep));
+                if (vb && ((in_w >> it) & 1)) v[4 + it] = ldg_nc16(vol0 + (ob + it * gstep));
               }
             }
             if (hp == 0) wait_stage_free();
@@ -370,10 +432,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kZRegsMma));
     const int me = warp - kZMmaWarp0;
     if (me < c.issuers) {
-      const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc48 = (1u << 4) | ((48u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_first = (1u << 4) | ((uint32_t)(G::n_of(G::PZ) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_desc0 = make_desc(smem_u32(ring), kZProw * 16, 128);
-      const uint64_t b_desc0 = make_desc(smem_u32(w_s), 144 * 16, 128);
+      const uint64_t b_desc0 = make_desc(smem_u32(w_s), G::BN * 16, 128);
       const uint32_t stage_u16 = (uint32_t)c.stage_bytes >> 4;
       mbar_wait(w_bar, 0);
       int t = 0, turn = 0, stage = 0, slot = 0;
@@ -386,7 +447,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         int b, z0, ya, yb;
         decode(u, b, z0, ya, yb);
         const int n_rows = (yb - ya) + 2;
-        const bool pl0 = z0 >= 1, pl3 = z0 + 2 < c.D;
+        const uint32_t pl_ok = planes_ok(z0);
         for (int j = 0; j < n_rows; ++j) {
           if (turn == me) {
             ZPROF_T(w0);
@@ -404,10 +465,12 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
             if (elect_one()) {
               const uint64_t da_st = (a_desc0 & 0xffffffff00000000ull) | da_lo;
               uint32_t accum = 0;
-              z_issue_plane<CHUNKS, 1, 48, 0>(d, da_st, b_desc0, idesc96, accum);          // z0   -> tiles 0 | 1
-              z_issue_plane<CHUNKS, 2, 0, 0>(d, da_st, b_desc0, idesc96, accum);           // z0+1 -> tiles 0 | 1
-              if (pl0) z_issue_plane<CHUNKS, 0, 96, 0>(d, da_st, b_desc0, idesc48, accum);  // z0-1 -> tile 0
-              if (pl3) z_issue_plane<CHUNKS, 3, 0, 0>(d + 48, da_st, b_desc0, idesc48, accum);   // z0+2 -> tile 1
+              // plane PZ (output plane z0 itself, always inside the volume) touches every tile of the step: its first
+              // MMA is the "accumulate = 0" one
+              static_assert(G::n_of(G::PZ) == G::SLOT_COLS && G::d_off(G::PZ) == 0, "the first-touch plane must cover the whole slot");
+              z_issue_plane<CHUNKS, G::PZ, G::BN, G::b_col(G::PZ), 0>(d, da_st, b_desc0, idesc_first, accum);
+              z_issue_other_planes<CHUNKS, CP, ZC, NKZ, 0, true>(d, da_st, b_desc0, pl_ok, accum);
+              z_issue_other_planes<CHUNKS, CP, ZC, NKZ, 0, false>(d, da_st, b_desc0, pl_ok, accum);
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
               progress[me] = t + c.issuers;  // this issuer's next step (steps are dealt round-robin to the issuers)
             }
@@ -441,8 +504,8 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         int b, z0, ya, yb;
         decode(u, b, z0, ya, yb);
         const int n_rows = (yb - ya) + 2;
-        const int zi = z0 - 1 + lane;                       // lanes 0-3: planes z0-1 .. z0+2
-        const bool pl_ok = lane < 4 && zi >= 0 && zi < c.D;
+        const int zi = z0 - G::PZ + lane;                   // lanes 0 .. NPL-1: one input plane each
+        const bool pl_ok = lane < G::NPL && zi >= 0 && zi < c.D;
         const char* plane = reinterpret_cast<const char*>(a.src) + ((size_t)b * c.D + zi) * zplane_bytes;
         for (int j = 0; j < n_rows; ++j, ++t) {
           // pace on the issuers' progress counters (plain shared-memory words: no barrier phase to miss, and the
@@ -460,13 +523,16 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       }
     }
   } else {
-    // =========================== EPILOGUE (set k = output plane z0 + k) ===========================
+    // ============ EPILOGUE (warp set k: output plane z0 + k when ZC = 2, channels 16 k .. 16 k + 15 when CP = 32) ======
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kZRegsEpilogue));
     const int k = (warp - kZEpilogueWarp0) >> 2;
+    if (k < kSets) {
+    const int pk = ZC == 2 ? k : 0;                  // output plane of this set
+    const int c0 = CP == 32 ? 16 * k : 0;            // first output channel of this set
     const int wq = warp & 3;
     const int x = wq * 32 + lane;                    // output column == TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(k * 48);
-    const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && a.cout == 16;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(pk * G::TILE_N + c0);
+    const bool vec_store = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && c0 + 16 <= a.cout;
     const bool col_ok = x < c.W;
     const bool has_bias = a.bias != nullptr;
     const size_t out_row_stride = (size_t)c.W * a.dst_cs;
@@ -484,9 +550,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
           v1 += __shfl_xor_sync(0xffffffffu, v1, off);
           v2 += __shfl_xor_sync(0xffffffffu, v2, off);
         }
-        if (lane == 0 && j < a.cout) {
-          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + j) * 2 + 0, (double)v1);
-          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + j) * 2 + 1, (double)v2);
+        if (lane == 0 && c0 + j < a.cout) {
+          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + c0 + j) * 2 + 0, (double)v1);
+          atomicAdd(a.dst_stats + ((size_t)b * a.dst_stat_stride + c0 + j) * 2 + 1, (double)v2);
         }
         s1[j] = s2[j] = 0.f;
       }
@@ -508,7 +574,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       // first two steps here and for step yo + 2 inside the loop
       mbar_wait(&step_bar[t & (kZStepBars - 1)], (uint32_t)(t >> 4) & 1u);
       mbar_wait(&step_bar[(t + 1) & (kZStepBars - 1)], (uint32_t)((t + 1) >> 4) & 1u);
-      __half* out_px = a.dst + (((size_t)b * c.D + z0 + k) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs;
+      __half* out_px = a.dst + (((size_t)b * c.D + z0 + pk) * c.H + ya) * out_row_stride + (size_t)x * a.dst_cs + c0;
       for (int yo = 0; yo < n_out; ++yo, out_px += out_row_stride) {
         const int tc = t + 2;
         ZPROF_T(w0);
@@ -523,9 +589,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
         // one TMEM round per row: the three 16-column groups are in flight together
         {
           uint32_t r0[16], r1[16], r2[16];
-          tmem_ld16_nowait(t_lane + (uint32_t)(slot_a * kZSlotCols + 0), r0);     // T[y-1], ky = 0
-          tmem_ld16_nowait(t_lane + (uint32_t)(slot_b * kZSlotCols + 16), r1);    // T[y],   ky = 1
-          tmem_ld16_nowait(t_lane + (uint32_t)(slot_c * kZSlotCols + 32), r2);    // T[y+1], ky = 2
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_a * kZSlotCols + 0), r0);           // T[y-1], ky = 0
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_b * kZSlotCols + CP), r1);          // T[y],   ky = 1
+          tmem_ld16_nowait(t_lane + (uint32_t)(slot_c * kZSlotCols + 2 * CP), r2);      // T[y+1], ky = 2
           tmem_wait_ld();
           // the tile of step t is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
           tc_fence_before();
@@ -537,7 +603,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
               float v0 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
               float v1 = (__uint_as_float(r0[j + 1]) + __uint_as_float(r1[j + 1])) + __uint_as_float(r2[j + 1]);
               if (has_bias) {       // only a convolution WITHOUT a following InstanceNorm keeps its bias (program.py)
-                const float2 bj = *reinterpret_cast<const float2*>(bias_s + j);
+                const float2 bj = *reinterpret_cast<const float2*>(bias_s + c0 + j);
                 v0 += bj.x;
                 v1 += bj.y;
               }
@@ -553,7 +619,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < a.cout) out_px[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
+                if (c0 + j < a.cout) out_px[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
         }
@@ -576,6 +642,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
       o[0] = zp[0]; o[1] = zp[1]; o[2] = clock64() - zt0;
     }
 #endif
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -585,21 +652,23 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
   }
 }
 
-// weights [cout][cin][kz][ky][kx] fp32 -> fp16 [kx][chunk][half][n = (2 - kz) * 48 + ky * 16 + co][8]
-__global__ void pack_weights_zrows_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout) {
+// weights [cout][cin][kz][ky][kx] fp32 -> fp16 [kx][chunk][half][n = (nkz - 1 - kz) * 3 cp + ky * cp + co][8]
+__global__ void pack_weights_zrows_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int cp,
+                                          int nkz) {
   const int chunks = cin / 16;
-  const size_t total = (size_t)3 * chunks * 2 * 144 * 8;
+  const int bn = nkz * 3 * cp;
+  const size_t total = (size_t)3 * chunks * 2 * bn * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int e = (int)(r % 8); r /= 8;
-    const int n = (int)(r % 144); r /= 144;
+    const int n = (int)(r % bn); r /= bn;
     const int h = (int)(r % 2); r /= 2;
     const int kc = (int)(r % chunks); r /= chunks;
     const int kx = (int)r;
-    const int kz = 2 - n / 48, ky = (n % 48) / 16, co = n % 16;
+    const int kz = nkz - 1 - n / (3 * cp), ky = (n % (3 * cp)) / cp, co = n % cp;
     const int ci = kc * 16 + h * 8 + e;
     float v = 0.f;
-    if (co < cout) v = w[((((size_t)co * cin + ci) * 3 + kz) * 3 + ky) * 3 + kx];
+    if (co < cout) v = w[((((size_t)co * cin + ci) * nkz + kz) * 3 + ky) * 3 + kx];
     out[i] = __float2half_rn(v);
   }
 }
@@ -614,13 +683,15 @@ bool zrows_supported(const ConvArgs& a) {
   }
   if (!enabled) return false;
   ZCfg c;
-  return plan_zrows(a, c);
+  if (!plan_zrows(a, c)) return false;
+  // FNNU_ZROWS=2: only the z-pair form (the older ky-folded kernel keeps the other shapes) — A/B measurements
+  return enabled == 1 || c.zc == 2;
 }
 
 int launch_pack_weights_zrows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s) {
   ZCfg c;
   if (!plan_zrows(a, c)) return FNNU_E_UNSUPPORTED;
-  pack_weights_zrows_kernel<<<64, 256, 0, s>>>(w_dev, (__half*)out, a.cin, a.cout);
+  pack_weights_zrows_kernel<<<64, 256, 0, s>>>(w_dev, (__half*)out, a.cin, a.cout, c.cp, c.nkz);
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;
 }
@@ -638,14 +709,24 @@ int launch_conv_zrows(const ConvArgs& a, cudaStream_t s) {
     set_error("conv_umma_zrows: unsupported shape");
     return FNNU_E_UNSUPPORTED;
   }
-  p.n_units = a.batch * (p.c.D / 2) * p.c.n_yseg;
+  p.n_units = a.batch * (p.c.D / p.c.zc) * p.c.n_yseg;
   const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-  if (p.c.chunks == 1) {
-    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_zrows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZSmemLimit));
-    conv_umma_zrows_kernel<1><<<grid, kZThreads, p.c.smem_bytes, s>>>(p);
-  } else {
-    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_zrows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZSmemLimit));
-    conv_umma_zrows_kernel<2><<<grid, kZThreads, p.c.smem_bytes, s>>>(p);
+  bool launched = false;
+#define FNNU_Z_CASE(CH, CPV, ZCV, NKZV)                                                                                       \
+  if (!launched && p.c.chunks == CH && p.c.cp == CPV && p.c.zc == ZCV && p.c.nkz == NKZV) {                                  \
+    /* the attribute is per device: set it on every launch (cheap) */                                                         \
+    FNNU_CUDA(cudaFuncSetAttribute(conv_umma_zrows_kernel<CH, CPV, ZCV, NKZV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                   kZSmemLimit));                                                                             \
+    conv_umma_zrows_kernel<CH, CPV, ZCV, NKZV><<<grid, kZThreads, p.c.smem_bytes, s>>>(p);                                    \
+    launched = true;                                                                                                          \
+  }
+  FNNU_Z_CASE(1, 16, 2, 3) FNNU_Z_CASE(2, 16, 2, 3)
+  FNNU_Z_CASE(1, 16, 1, 3) FNNU_Z_CASE(2, 16, 1, 3) FNNU_Z_CASE(1, 16, 1, 1) FNNU_Z_CASE(2, 16, 1, 1)
+  FNNU_Z_CASE(1, 32, 1, 3) FNNU_Z_CASE(2, 32, 1, 3) FNNU_Z_CASE(1, 32, 1, 1) FNNU_Z_CASE(2, 32, 1, 1)
+#undef FNNU_Z_CASE
+  if (!launched) {
+    set_error("conv_umma_zrows: no instantiation for chunks=%d cp=%d zc=%d nkz=%d", p.c.chunks, p.c.cp, p.c.zc, p.c.nkz);
+    return FNNU_E_UNSUPPORTED;
   }
   FNNU_LAUNCH_CHECK();
   return FNNU_OK;

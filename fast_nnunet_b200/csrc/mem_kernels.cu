@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(
   for (int c = C; c < cs; ++c) dst[c] = __float2half_rn(0.f);
 }
 
-// Single-channel volumes (CT): one thread converts 8 consecutive z voxels -> one 16-byte store.
-// Mirrored-z copies read the 8 source voxels in reverse.  Requires pZ % 8 == 0 and cs == 1.  Same grid layout.
+// Single-channel volumes (CT): one thread reads 8 consecutive z voxels of the tile ONCE (two 128-bit loads) and writes
+// every mirrored copy (one 16-byte store per copy; z-mirrored copies get the 8 values in reverse order).
+// Requires pZ % 8 == 0 and cs == 1.  grid: x = chunks of 256 over (y, z / 8), y = tile plane x, z = tile.
 __global__ void __launch_bounds__(256) gather_tiles_c1_vec8_kernel(
     const float* __restrict__ vol, int X, int Y, int Z, const int32_t* __restrict__ starts, int n_tiles, int pX,
     int pY, int pZ, FlipList flips, int n_flips, __half* __restrict__ out) {
@@ -74,15 +75,9 @@ __global__ void __launch_bounds__(256) gather_tiles_c1_vec8_kernel(
   const int y = (int)(idx / (uint32_t)zq);
   const int z = (int)(idx - (uint32_t)y * (uint32_t)zq) << 3;
   const int x = blockIdx.y;
-  const int n = blockIdx.z;
-  const int t = n / n_flips;
-  const int f = flips.m[n - t * n_flips];
+  const int t = blockIdx.z;
   const int sx = starts[t * 3 + 0], sy = starts[t * 3 + 1], sz = starts[t * 3 + 2];
-  const int gx = sx + ((f & 1) ? pX - 1 - x : x);
-  const int gy = sy + ((f & 2) ? pY - 1 - y : y);
-  const bool rz = (f & 4) != 0;
-  const int gz = sz + (rz ? pZ - 8 - z : z);
-  const float* src = vol + ((size_t)gx * Y + gy) * Z + gz;
+  const float* src = vol + ((size_t)(sx + x) * Y + (sy + y)) * Z + (sz + z);
   float v[8];
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -92,11 +87,26 @@ __global__ void __launch_bounds__(256) gather_tiles_c1_vec8_kernel(
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k);
   }
-  __half2 h[4];
+  __half2 fwd[4], rev[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    h[k] = rz ? __floats2half2_rn(v[7 - 2 * k], v[6 - 2 * k]) : __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-  *reinterpret_cast<uint4*>(out + ((size_t)n * pX + x) * pY * pZ + (size_t)y * pZ + z) = *reinterpret_cast<uint4*>(h);
+  for (int k = 0; k < 4; ++k) {
+    fwd[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    rev[k] = __floats2half2_rn(v[7 - 2 * k], v[6 - 2 * k]);
+  }
+  const size_t pvox = (size_t)pX * pY * pZ;
+  __half* out_t = out + (size_t)t * n_flips * pvox;
+#pragma unroll
+  for (int fi = 0; fi < 8; ++fi) {
+    if (fi < n_flips) {
+      const int f = flips.m[fi];
+      const int dx = (f & 1) ? pX - 1 - x : x;
+      const int dy = (f & 2) ? pY - 1 - y : y;
+      const bool rz = (f & 4) != 0;
+      const int dz = rz ? pZ - 8 - z : z;
+      *reinterpret_cast<uint4*>(out_t + (size_t)fi * pvox + ((size_t)dx * pY + dy) * pZ + dz) =
+          rz ? *reinterpret_cast<const uint4*>(rev) : *reinterpret_cast<const uint4*>(fwd);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,110 +287,133 @@ __device__ __forceinline__ void load_heads(const __half* p, float* out) {
   }
 }
 
-template <int HC, int VZ>
-__global__ void __launch_bounds__(256) accumulate_cluster_kernel(
+// CONTIG: the prediction stride equals HC, so a thread's VZ voxels x HC heads are VZ * HC * 2 contiguous bytes.
+// SINGLE: heads <= HC, one chunk per voxel (no head-chunk index arithmetic).
+template <int HC, int VZ, bool CONTIG, bool SINGLE>
+__global__ void __launch_bounds__(256, (HC <= 2 ? 4 : (HC <= 4 ? 3 : 2))) accumulate_cluster_kernel(
     const __half* __restrict__ preds_all, int ps, int heads, TileCluster tc, int pX, int pY, int pZ, FlipList flips,
     int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
   // grid: x = chunks of 256 over (y, z quads) of one box plane, y = box plane: 32-bit index arithmetic only
+  constexpr int NQ = VZ * HC / 8;            // 16-byte loads per flip and thread
+  constexpr int G = 8 / NQ;                  // flips whose loads are in flight together (8 x 16 bytes per thread)
+  constexpr int PQ = HC >= 8 ? HC / 8 : 1;   // 16-byte pieces per voxel (non-contiguous case)
+  static_assert(NQ >= 1 && NQ <= 4, "accumulate_cluster_kernel: unsupported (HC, VZ)");
+  // Head chunks are the FASTEST thread index: with more heads than HC, neighbouring lanes read neighbouring
+  // 16 / 32-byte pieces of the same voxel, so a warp's load covers whole 128-byte lines.
   const int zq = tc.bz / VZ;
-  const size_t pvox = (size_t)pX * pY * pZ;
+  const int n_hc = SINGLE ? 1 : (heads + HC - 1) / HC;
+  const uint32_t pv32 = (uint32_t)pX * (uint32_t)pY * (uint32_t)pZ;
   const size_t hstride = (size_t)X * Y * Z;
   const float nf = (float)n_flips;
   const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
-  if (idx >= (uint32_t)(tc.by * zq)) return;
+  if (idx >= (uint32_t)(tc.by * zq * n_hc)) return;
+  const uint32_t vox = SINGLE ? idx : idx / (uint32_t)n_hc;
+  const int h0 = SINGLE ? 0 : (int)(idx - vox * (uint32_t)n_hc) * HC;
+  const int yy = (int)(vox / (uint32_t)zq);
+  const int gz = tc.oz + (int)(vox - (uint32_t)yy * (uint32_t)zq) * VZ;
+  const int gy = tc.oy + yy;
+  const int gx = tc.ox + (int)blockIdx.y;
+  float* const a0 = acc + ((size_t)gx * Y + gy) * Z + gz;
   {
-    const int yy = (int)(idx / (uint32_t)zq);
-    const int gz = tc.oz + (int)(idx - (uint32_t)yy * (uint32_t)zq) * VZ;
-    const int gy = tc.oy + yy;
-    const int gx = tc.ox + (int)blockIdx.y;
-    float* const a0 = acc + ((size_t)gx * Y + gy) * Z + gz;
-    for (int h0 = 0; h0 < heads; h0 += HC) {
-      float r[VZ][HC];
-      bool any = false;
-      for (int t = 0; t < tc.n; ++t) {
-        const int lx = gx - tc.sx[t], ly = gy - tc.sy[t], lz = gz - tc.sz[t];
-        if ((unsigned)lx >= (unsigned)pX || (unsigned)ly >= (unsigned)pY || (unsigned)lz >= (unsigned)pZ) continue;
-        if (!any) {
-          any = true;
-#pragma unroll
-          for (int j = 0; j < HC; ++j) {
-            if (h0 + j < heads) {
-              if constexpr (VZ == 4) {
-                const float4 v = *reinterpret_cast<const float4*>(a0 + (size_t)(h0 + j) * hstride);
-                r[0][j] = v.x; r[1][j] = v.y; r[2][j] = v.z; r[3][j] = v.w;
-              } else {
-                const float2 v = *reinterpret_cast<const float2*>(a0 + (size_t)(h0 + j) * hstride);
-                r[0][j] = v.x; r[1][j] = v.y;
-              }
-            }
-          }
-        }
-        const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pvox * ps + h0;
-        const uint32_t pv32 = (uint32_t)pvox;
-        float s[VZ][HC];
-#pragma unroll
-        for (int f = 0; f < 8; ++f) {
-          if (f < n_flips) {
-            const int m = flips.m[f];
-            const int fx = (m & 1) ? pX - 1 - lx : lx;
-            const int fy = (m & 2) ? pY - 1 - ly : ly;
-            const bool rz = (m & 4) != 0;
-            const int fz = rz ? pZ - VZ - lz : lz;
-            // offsets inside one tile's 8 predictions fit 32 bits (8 x 2.1 M voxels x 64 heads = 1.07 G elements)
-            const __half* src = preds + (size_t)(((uint32_t)f * pv32 + (uint32_t)((fx * pY + fy) * pZ + fz)) * (uint32_t)ps);
-            if (HC * VZ <= 16 && ps == HC) {
-              // the thread's VZ voxels x HC heads are contiguous: one or two 128-bit loads
-              float blockv[VZ * HC];
-#pragma unroll
-              for (int q = 0; q < VZ * HC / 8; ++q) load_heads<8>(src + q * 8, blockv + q * 8);
-#pragma unroll
-              for (int v = 0; v < VZ; ++v)
-#pragma unroll
-                for (int j = 0; j < HC; ++j) {
-                  const float pv = rz ? blockv[(VZ - 1 - v) * HC + j] : blockv[v * HC + j];
-                  s[v][j] = (f == 0) ? pv : __fadd_rn(s[v][j], pv);
-                }
-            } else {
-#pragma unroll
-              for (int v = 0; v < VZ; ++v) {
-                float piece[HC];
-                load_heads<HC>(src + (size_t)(rz ? VZ - 1 - v : v) * ps, piece);
-#pragma unroll
-                for (int j = 0; j < HC; ++j) s[v][j] = (f == 0) ? piece[j] : __fadd_rn(s[v][j], piece[j]);
-              }
-            }
-          }
-        }
-        float g[VZ];
-#pragma unroll
-        for (int v = 0; v < VZ; ++v) g[v] = 1.f;
-        if (gauss) {
-          const __half* gp = gauss + ((size_t)lx * pY + ly) * pZ + lz;
-#pragma unroll
-          for (int v = 0; v < VZ; v += 2) {
-            const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gp + v));
-            g[v] = gv.x; g[v + 1] = gv.y;
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < VZ; ++v)
-#pragma unroll
-          for (int j = 0; j < HC; ++j) {
-            float c = s[v][j];
-            if (n_flips > 1) c = __fdiv_rn(c, nf);
-            if (gauss) c = __fmul_rn(c, g[v]);
-            r[v][j] = __fadd_rn(r[v][j], c);
-          }
-      }
-      if (any) {
+    float r[VZ][HC];
+    bool any = false;
+    for (int t = 0; t < tc.n; ++t) {
+      const int lx = gx - tc.sx[t], ly = gy - tc.sy[t], lz = gz - tc.sz[t];
+      if ((unsigned)lx >= (unsigned)pX || (unsigned)ly >= (unsigned)pY || (unsigned)lz >= (unsigned)pZ) continue;
+      if (!any) {
+        any = true;
 #pragma unroll
         for (int j = 0; j < HC; ++j) {
           if (h0 + j < heads) {
-            if constexpr (VZ == 4)
-              *reinterpret_cast<float4*>(a0 + (size_t)(h0 + j) * hstride) = make_float4(r[0][j], r[1][j], r[2][j], r[3][j]);
-            else
-              *reinterpret_cast<float2*>(a0 + (size_t)(h0 + j) * hstride) = make_float2(r[0][j], r[1][j]);
+            if constexpr (VZ == 4) {
+              const float4 v = *reinterpret_cast<const float4*>(a0 + (size_t)(h0 + j) * hstride);
+              r[0][j] = v.x; r[1][j] = v.y; r[2][j] = v.z; r[3][j] = v.w;
+            } else {
+              const float2 v = *reinterpret_cast<const float2*>(a0 + (size_t)(h0 + j) * hstride);
+              r[0][j] = v.x; r[1][j] = v.y;
+            }
           }
+        }
+      }
+      float g[VZ];
+#pragma unroll
+      for (int v = 0; v < VZ; ++v) g[v] = 1.f;
+      if (gauss) {
+        const __half* gp = gauss + ((size_t)lx * pY + ly) * pZ + lz;
+#pragma unroll
+        for (int v = 0; v < VZ; v += 2) {
+          const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gp + v));
+          g[v] = gv.x; g[v + 1] = gv.y;
+        }
+      }
+      const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pv32 * ps + h0;
+      float s[VZ][HC];
+#pragma unroll
+      for (int f0 = 0; f0 < 8; f0 += G) {
+        if (f0 < n_flips) {
+          // ---- all loads of G flips first (independent, 8 x 16 bytes in flight per thread) ...
+          uint4 raw[G][NQ];
+          bool rzs[G];
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int f = f0 + i;
+            const int m = flips.m[f];
+            const int fx = (m & 1) ? pX - 1 - lx : lx;
+            const int fy = (m & 2) ? pY - 1 - ly : ly;
+            rzs[i] = (m & 4) != 0;
+            const int fz = rzs[i] ? pZ - VZ - lz : lz;
+            // offsets inside one tile's predictions fit 32 bits (8 x 2.1 M voxels x 64 heads = 1.07 G elements)
+            const __half* src = preds + (size_t)(((uint32_t)f * pv32 + (uint32_t)((fx * pY + fy) * pZ + fz)) * (uint32_t)ps);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              raw[i][q] = make_uint4(0, 0, 0, 0);
+              if (f < n_flips) {
+                if constexpr (CONTIG) raw[i][q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                else raw[i][q] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(q / PQ) * ps) + (q % PQ));
+              }
+            }
+          }
+          // ---- ... then the sums, flip after flip (the reference's order)
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int f = f0 + i;
+            if (f < n_flips) {
+              const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&raw[i][0]);      // one half2 per word
+#pragma unroll
+              for (int v = 0; v < VZ; ++v) {
+#pragma unroll
+                for (int j = 0; j < HC; j += 2) {
+                  // the mirrored copy stores the voxels in reverse: select the VALUE (both indices are compile-time
+                  // constants, so the loaded words stay in registers)
+                  const uint32_t wf = w32[(v * HC + j) >> 1], wr = w32[((VZ - 1 - v) * HC + j) >> 1];
+                  const uint32_t w = rzs[i] ? wr : wf;
+                  const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                  s[v][j] = (f == 0) ? pv.x : __fadd_rn(s[v][j], pv.x);
+                  s[v][j + 1] = (f == 0) ? pv.y : __fadd_rn(s[v][j + 1], pv.y);
+                }
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VZ; ++v)
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          float c = s[v][j];
+          if (n_flips > 1) c = __fdiv_rn(c, nf);
+          if (gauss) c = __fmul_rn(c, g[v]);
+          r[v][j] = __fadd_rn(r[v][j], c);
+        }
+    }
+    if (any) {
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        if (h0 + j < heads) {
+          if constexpr (VZ == 4)
+            *reinterpret_cast<float4*>(a0 + (size_t)(h0 + j) * hstride) = make_float4(r[0][j], r[1][j], r[2][j], r[3][j]);
+          else
+            *reinterpret_cast<float2*>(a0 + (size_t)(h0 + j) * hstride) = make_float2(r[0][j], r[1][j]);
         }
       }
     }
@@ -513,26 +546,34 @@ __global__ void __launch_bounds__(256) finalize_vec4_kernel(const float* __restr
     const float wv[4] = {w.x, w.y, w.z, w.w};
     float best[4];
     uint32_t arg[4] = {0, 0, 0, 0};
-#pragma unroll 4
-    for (int h = 0; h < heads; ++h) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(acc + (size_t)h * hs) + q);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      __half hv[4];
+    for (int h0 = 0; h0 < heads; h0 += 8) {
+      float4 a8[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        hv[k] = __float2half_rn(__fdiv_rn(av[k], wv[k]));
-        const float r = __half2float(hv[k]);
-        if (isinf(r)) saw_inf = true;
-        if (h == 0 || r > best[k]) {      // strict '>' keeps the first maximum (numpy argmax)
-          best[k] = r;
-          arg[k] = (uint32_t)h;
+      for (int i = 0; i < 8; ++i)       // eight independent 128-bit loads in flight per thread
+        if (h0 + i < heads) a8[i] = __ldg(reinterpret_cast<const float4*>(acc + (size_t)(h0 + i) * hs) + q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int h = h0 + i;
+        if (h < heads) {
+          const float av[4] = {a8[i].x, a8[i].y, a8[i].z, a8[i].w};
+          __half hv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            hv[k] = __float2half_rn(__fdiv_rn(av[k], wv[k]));
+            const float r = __half2float(hv[k]);
+            if (isinf(r)) saw_inf = true;
+            if (h == 0 || r > best[k]) {      // strict '>' keeps the first maximum (numpy argmax)
+              best[k] = r;
+              arg[k] = (uint32_t)h;
+            }
+          }
+          if (logits) {
+            uint2 o;
+            o.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
+            o.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
+            reinterpret_cast<uint2*>(logits + (size_t)h * nvox)[q] = o;
+          }
         }
-      }
-      if (logits) {
-        uint2 o;
-        o.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
-        o.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
-        reinterpret_cast<uint2*>(logits + (size_t)h * nvox)[q] = o;
       }
     }
     if (labels) reinterpret_cast<uint32_t*>(labels)[q] = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
@@ -585,7 +626,7 @@ extern "C" int fnnu_gather_tiles(const float* volume, int channels, const int vo
   for (int i = 0; i < 8; ++i) fl.m[i] = i < n_flips ? (flip_masks[i] & 7) : 0;
   FNNU_CHECK_ARG(patch[0] <= 65535 && n_tiles * n_flips <= 65535, "gather: grid extents");
   if (channels == 1 && c_stride == 1 && patch[2] % 8 == 0 && ((uintptr_t)out % 16) == 0) {
-    const dim3 g8((unsigned)((patch[1] * (patch[2] / 8) + 255) / 256), (unsigned)patch[0], (unsigned)(n_tiles * n_flips));
+    const dim3 g8((unsigned)((patch[1] * (patch[2] / 8) + 255) / 256), (unsigned)patch[0], (unsigned)n_tiles);
     gather_tiles_c1_vec8_kernel<<<g8, 256, 0, (cudaStream_t)stream>>>(
         volume, vol_dims[0], vol_dims[1], vol_dims[2], starts_dev, n_tiles, patch[0], patch[1], patch[2], fl, n_flips,
         (__half*)out);
@@ -674,14 +715,20 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
       tc.ox = lo[0]; tc.oy = lo[1]; tc.oz = lo[2];
       tc.bx = hi[0] - lo[0]; tc.by = hi[1] - lo[1]; tc.bz = hi[2] - lo[2];
       FNNU_CHECK_ARG((size_t)8 * pvox * p_stride < ((size_t)1 << 32) && tc.bx <= 65535, "accumulate: tile too large for the 32-bit offsets");
-      const dim3 grid((unsigned)((tc.by * (tc.bz / vz) + 255) / 256), (unsigned)tc.bx);
+      const int n_hc = (heads + hc - 1) / hc;
+      const dim3 grid((unsigned)((tc.by * (tc.bz / vz) * n_hc + 255) / 256), (unsigned)tc.bx);
       const __half* pr = (const __half*)preds;
       const __half* gs = (const __half*)gaussian;
       float* ac = (float*)acc;
-      if (hc == 2) accumulate_cluster_kernel<2, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
-      else if (hc == 4) accumulate_cluster_kernel<4, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
-      else if (hc == 8) accumulate_cluster_kernel<8, 4><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
-      else accumulate_cluster_kernel<16, 2><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z);
+#define FNNU_ACC_LAUNCH(HCV, VZV, CT, SG) accumulate_cluster_kernel<HCV, VZV, CT, SG><<<grid, 256, 0, s>>>(pr, p_stride, heads, tc, pX, pY, pZ, fl, n_flips, gs, ac, X, Y, Z)
+      const bool contig = p_stride == hc;
+      if (hc == 2) FNNU_ACC_LAUNCH(2, 4, true, true);
+      else if (hc == 4) FNNU_ACC_LAUNCH(4, 4, true, true);
+      else if (hc == 8 && contig) FNNU_ACC_LAUNCH(8, 4, true, true);
+      else if (hc == 8) FNNU_ACC_LAUNCH(8, 4, false, false);
+      else if (contig) FNNU_ACC_LAUNCH(16, 2, true, true);
+      else FNNU_ACC_LAUNCH(16, 2, false, false);
+#undef FNNU_ACC_LAUNCH
       FNNU_LAUNCH_CHECK();
       ++g_mem_launches;
     }

@@ -30,6 +30,9 @@ ZROWS_W72_H9 = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(4, 18, 72),
 TINY_ONNX = dict(cls=M.PLAIN, in_ch=1, heads=3, patch=(16, 16, 16),
                  kw=M.plain_arch_kwargs([8, 16, 16], [[1, 3, 3], [3, 3, 3], [3, 3, 3]], [[1, 1, 1], [1, 2, 2], [2, 2, 2]],
                                         [2, 1, 2], [1, 2]))
+# odd depth: one output plane per pass (ZC = 1) with the full 3x3x3 kernel; anisotropic second stage keeps D = 5
+ZROWS_ODD_D = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(5, 16, 128),
+                   kw=M.plain_arch_kwargs([16, 32], [[3, 3, 3]] * 2, [[1, 1, 1], [1, 2, 2]]))
 STUDENT = dict(cls=M.PLAIN, in_ch=1, heads=2, patch=(128, 128, 128),
                kw=M.plain_arch_kwargs([16, 32, 64, 128, 160, 160], [[3, 3, 3]] * 6, [[1, 1, 1]] + [[2, 2, 2]] * 5))
 

@@ -23,7 +23,16 @@ sd, _ = nets.make(spec, randomize_affine=False)
 dev = torch.device('cuda', 0)
 cn = CompiledNetwork(spec['cls'], spec['kw'], spec['in_ch'], spec['heads'], spec['patch'])
 cn.load_state_dict(sd)
-eng = cn.engine(dev, batch)
+n_ops = int(os.environ.get('TIME_OPS_TRUNCATE', '0'))
+if n_ops:
+    # run only the first n operators (the instrumented builds report the LAST row-streaming launch)
+    from fast_nnunet_b200.engine import NetworkEngine
+    from fast_nnunet_b200.program import build_program
+    prog = build_program(spec['cls'], sd, spec['kw'], spec['in_ch'], spec['heads'], spec['patch'])
+    prog.ops = prog.ops[:n_ops]
+    eng = NetworkEngine(prog, batch, dev)
+else:
+    eng = cn.engine(dev, batch)
 prog = eng.program
 inp = eng.buffer_tensor(prog.input_buffer, batch)
 inp.copy_(torch.randn(inp.shape, device=dev).half())
@@ -65,7 +74,7 @@ try:
         buf = (ctypes.c_longlong * 32)()
         lib.fnnu_debug_zrows_prof(buf)
         v = list(buf)
-        print('zrows role cycles of CTA 0, LAST zrows launch (dec5.1):')
+        print('zrows role cycles of CTA 0, LAST zrows launch:')
         print(f'  producer warp 0: wait stage-free {v[0]}, stages filled {v[1]}, total {v[2]}')
         for m in range(2):
             o = 8 + m * 8
