@@ -24,9 +24,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    spec = nets.SMALL_PLAIN16
+    if os.environ.get('SHARDED_CHECK', 'student') == 'toy':
+        spec, vol = nets.SMALL_PLAIN16, (112, 40, 48)
+    else:
+        # cfg-2-shaped slabs: the distilled student, 128^3 patches at pitch 64 (3 x 2 x 2 tiles x 8 mirror passes)
+        spec, vol = nets.STUDENT, (256, 192, 192)
     sd, _ = nets.make(spec)
-    x = nets.ct_like_volume((112, 40, 48), 1)
+    x = nets.ct_like_volume(vol, 1)         # a HOST tensor: every rank uploads only the planes its tiles read
     with tempfile.TemporaryDirectory() as tmp:
         folder = M.write_model_folder(os.path.join(tmp, f'r{rank}', 'nnUNetTrainer__nnUNetPlans__3d_fullres'), spec['cls'],
                                       spec['kw'], spec['patch'], sd, 1, 2)

@@ -111,3 +111,39 @@ def test_exchange_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, (70, 24, 20), (16, 16, 16), 2, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f'r{r}').read() == 'ok'
+
+
+def _worker_subgroup(rank, world, port, vol, patch, heads, result_dir):
+    """Ranks 1..world-1 form a sub-group (group rank = global rank - 1): plan ranks are GROUP ranks and must be
+    translated to global ranks for the point-to-point operations."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        members = list(range(1, world))
+        group = dist.new_group(ranks=members)
+        if rank in members:
+            grank, gworld = dist.get_rank(group), dist.get_world_size(group)
+            assert grank == rank - 1 and sharding.global_rank(group, grank) == rank
+            starts = sw.tile_starts(vol, patch, 0.5)
+            plan = sharding.plan_shards(starts, patch, vol, gworld)
+            acc = _local_acc(plan, grank, vol, patch, starts, heads)
+            sharding.exchange_halos(acc, plan, grank, lambda d, s: d.add_(s), group)
+            a, b = plan.owned[grank]
+            l0 = plan.local[grank][0]
+            want = _expected(vol, patch, starts, heads)[:, a:b]
+            ok = torch.allclose(acc[:, a - l0:b - l0], want, atol=1e-5)
+        else:
+            ok = True
+        with open(os.path.join(result_dir, f'r{rank}'), 'w') as f:
+            f.write('ok' if ok else 'bad')
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_gloo_subgroup(tmp_path):
+    world = 3
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_worker_subgroup, args=(world, port, (70, 24, 20), (16, 16, 16), 2, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f'r{r}').read() == 'ok'
