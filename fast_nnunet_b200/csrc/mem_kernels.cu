@@ -287,17 +287,21 @@ __device__ __forceinline__ void load_heads(const __half* p, float* out) {
   }
 }
 
-// CONTIG: the prediction stride equals HC, so a thread's VZ voxels x HC heads are VZ * HC * 2 contiguous bytes.
+// CONTIG: the prediction stride equals HC, so a thread's VZ voxels x HC heads are VZ * HC * 2 contiguous bytes (needs
+// tile z starts that are multiples of VZ).  !CONTIG: every voxel's HC heads are one aligned 16 / 32-byte piece, loaded
+// voxel by voxel, so tile starts may be ANY integer (cfg 5's tiles start at 46, 139, 185 ...): a thread's VZ
+// accumulator voxels are aligned in the ACCUMULATOR, and each of them checks its own coverage.
 // SINGLE: heads <= HC, one chunk per voxel (no head-chunk index arithmetic).
 template <int HC, int VZ, bool CONTIG, bool SINGLE>
 __global__ void __launch_bounds__(256, (HC <= 2 ? 4 : (HC <= 4 ? 3 : 2))) accumulate_cluster_kernel(
     const __half* __restrict__ preds_all, int ps, int heads, TileCluster tc, int pX, int pY, int pZ, FlipList flips,
     int n_flips, const __half* __restrict__ gauss, float* __restrict__ acc, int X, int Y, int Z) {
-  // grid: x = chunks of 256 over (y, z quads) of one box plane, y = box plane: 32-bit index arithmetic only
+  // grid: x = chunks of 256 over (y, z groups[, head chunks]) of one box plane, y = box plane: 32-bit index arithmetic
   constexpr int NQ = VZ * HC / 8;            // 16-byte loads per flip and thread
   constexpr int G = 8 / NQ;                  // flips whose loads are in flight together (8 x 16 bytes per thread)
   constexpr int PQ = HC >= 8 ? HC / 8 : 1;   // 16-byte pieces per voxel (non-contiguous case)
   static_assert(NQ >= 1 && NQ <= 4, "accumulate_cluster_kernel: unsupported (HC, VZ)");
+  static_assert(CONTIG || HC >= 8, "voxel-by-voxel loads need at least 16 bytes of heads per voxel");
   // Head chunks are the FASTEST thread index: with more heads than HC, neighbouring lanes read neighbouring
   // 16 / 32-byte pieces of the same voxel, so a warp's load covers whole 128-byte lines.
   const int zq = tc.bz / VZ;
@@ -310,94 +314,121 @@ __global__ void __launch_bounds__(256, (HC <= 2 ? 4 : (HC <= 4 ? 3 : 2))) accumu
   const uint32_t vox = SINGLE ? idx : idx / (uint32_t)n_hc;
   const int h0 = SINGLE ? 0 : (int)(idx - vox * (uint32_t)n_hc) * HC;
   const int yy = (int)(vox / (uint32_t)zq);
-  const int gz = tc.oz + (int)(vox - (uint32_t)yy * (uint32_t)zq) * VZ;
+  const int gz = tc.oz + (int)(vox - (uint32_t)yy * (uint32_t)zq) * VZ;     // multiple of VZ in the accumulator
   const int gy = tc.oy + yy;
   const int gx = tc.ox + (int)blockIdx.y;
   float* const a0 = acc + ((size_t)gx * Y + gy) * Z + gz;
-  {
-    float r[VZ][HC];
-    bool any = false;
-    for (int t = 0; t < tc.n; ++t) {
-      const int lx = gx - tc.sx[t], ly = gy - tc.sy[t], lz = gz - tc.sz[t];
-      if ((unsigned)lx >= (unsigned)pX || (unsigned)ly >= (unsigned)pY || (unsigned)lz >= (unsigned)pZ) continue;
-      if (!any) {
-        any = true;
+  float r[VZ][HC];
+  bool any = false;
+  for (int t = 0; t < tc.n; ++t) {
+    const int lx = gx - tc.sx[t], ly = gy - tc.sy[t], lz = gz - tc.sz[t];
+    if ((unsigned)lx >= (unsigned)pX || (unsigned)ly >= (unsigned)pY) continue;
+    bool vok[VZ];           // voxel v of this thread lies inside tile t
+    bool some = false;
 #pragma unroll
-        for (int j = 0; j < HC; ++j) {
-          if (h0 + j < heads) {
-            if constexpr (VZ == 4) {
-              const float4 v = *reinterpret_cast<const float4*>(a0 + (size_t)(h0 + j) * hstride);
-              r[0][j] = v.x; r[1][j] = v.y; r[2][j] = v.z; r[3][j] = v.w;
-            } else {
-              const float2 v = *reinterpret_cast<const float2*>(a0 + (size_t)(h0 + j) * hstride);
-              r[0][j] = v.x; r[1][j] = v.y;
-            }
+    for (int v = 0; v < VZ; ++v) {
+      vok[v] = (unsigned)(lz + v) < (unsigned)pZ;
+      some = some || vok[v];
+    }
+    if (CONTIG ? !vok[0] : !some) continue;       // CONTIG: lz is a multiple of VZ, all or nothing
+    if (!any) {
+      any = true;
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        if (h0 + j < heads) {
+          if constexpr (VZ == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(a0 + (size_t)(h0 + j) * hstride);
+            r[0][j] = v.x; r[1][j] = v.y; r[2][j] = v.z; r[3][j] = v.w;
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(a0 + (size_t)(h0 + j) * hstride);
+            r[0][j] = v.x; r[1][j] = v.y;
           }
         }
       }
-      float g[VZ];
+    }
+    float g[VZ];
 #pragma unroll
-      for (int v = 0; v < VZ; ++v) g[v] = 1.f;
-      if (gauss) {
-        const __half* gp = gauss + ((size_t)lx * pY + ly) * pZ + lz;
+    for (int v = 0; v < VZ; ++v) g[v] = 1.f;
+    if (gauss) {
+      const __half* gp = gauss + ((size_t)lx * pY + ly) * pZ + lz;
+      if constexpr (CONTIG) {
 #pragma unroll
         for (int v = 0; v < VZ; v += 2) {
           const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gp + v));
           g[v] = gv.x; g[v + 1] = gv.y;
         }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VZ; ++v)
+          if (vok[v]) g[v] = __half2float(gp[v]);
       }
-      const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pv32 * ps + h0;
-      float s[VZ][HC];
+    }
+    const __half* __restrict__ preds = preds_all + (size_t)tc.idx[t] * n_flips * pv32 * ps + h0;
+    float s[VZ][HC];
 #pragma unroll
-      for (int f0 = 0; f0 < 8; f0 += G) {
-        if (f0 < n_flips) {
-          // ---- all loads of G flips first (independent, 8 x 16 bytes in flight per thread) ...
-          uint4 raw[G][NQ];
-          bool rzs[G];
+    for (int f0 = 0; f0 < 8; f0 += G) {
+      if (f0 < n_flips) {
+        // ---- all loads of G flips first (independent, 8 x 16 bytes in flight per thread) ...
+        uint4 raw[G][NQ];
+        bool rzs[G];
 #pragma unroll
-          for (int i = 0; i < G; ++i) {
-            const int f = f0 + i;
-            const int m = flips.m[f];
-            const int fx = (m & 1) ? pX - 1 - lx : lx;
-            const int fy = (m & 2) ? pY - 1 - ly : ly;
-            rzs[i] = (m & 4) != 0;
+        for (int i = 0; i < G; ++i) {
+          const int f = f0 + i;
+          const int m = flips.m[f];
+          const int fx = (m & 1) ? pX - 1 - lx : lx;
+          const int fy = (m & 2) ? pY - 1 - ly : ly;
+          rzs[i] = (m & 4) != 0;
+          // offsets inside one tile's predictions fit 32 bits (8 x 2.1 M voxels x 64 heads = 1.07 G elements)
+          const uint32_t row = (uint32_t)f * pv32 + (uint32_t)((fx * pY + fy) * pZ);
+          if constexpr (CONTIG) {
             const int fz = rzs[i] ? pZ - VZ - lz : lz;
-            // offsets inside one tile's predictions fit 32 bits (8 x 2.1 M voxels x 64 heads = 1.07 G elements)
-            const __half* src = preds + (size_t)(((uint32_t)f * pv32 + (uint32_t)((fx * pY + fy) * pZ + fz)) * (uint32_t)ps);
+            const __half* src = preds + (size_t)((row + (uint32_t)fz) * (uint32_t)ps);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
               raw[i][q] = make_uint4(0, 0, 0, 0);
-              if (f < n_flips) {
-                if constexpr (CONTIG) raw[i][q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
-                else raw[i][q] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(q / PQ) * ps) + (q % PQ));
+              if (f < n_flips) raw[i][q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const int v = q / PQ;                        // piece q belongs to accumulator voxel v
+              raw[i][q] = make_uint4(0, 0, 0, 0);
+              if (f < n_flips && vok[v]) {
+                const int fz = rzs[i] ? pZ - 1 - (lz + v) : lz + v;
+                raw[i][q] = __ldg(reinterpret_cast<const uint4*>(preds + (size_t)((row + (uint32_t)fz) * (uint32_t)ps)) + (q % PQ));
               }
             }
           }
-          // ---- ... then the sums, flip after flip (the reference's order)
+        }
+        // ---- ... then the sums, flip after flip (the reference's order)
 #pragma unroll
-          for (int i = 0; i < G; ++i) {
-            const int f = f0 + i;
-            if (f < n_flips) {
-              const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&raw[i][0]);      // one half2 per word
+        for (int i = 0; i < G; ++i) {
+          const int f = f0 + i;
+          if (f < n_flips) {
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&raw[i][0]);      // one half2 per word
 #pragma unroll
-              for (int v = 0; v < VZ; ++v) {
+            for (int v = 0; v < VZ; ++v) {
 #pragma unroll
-                for (int j = 0; j < HC; j += 2) {
+              for (int j = 0; j < HC; j += 2) {
+                uint32_t w = w32[(v * HC + j) >> 1];
+                if constexpr (CONTIG) {
                   // the mirrored copy stores the voxels in reverse: select the VALUE (both indices are compile-time
                   // constants, so the loaded words stay in registers)
-                  const uint32_t wf = w32[(v * HC + j) >> 1], wr = w32[((VZ - 1 - v) * HC + j) >> 1];
-                  const uint32_t w = rzs[i] ? wr : wf;
-                  const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                  s[v][j] = (f == 0) ? pv.x : __fadd_rn(s[v][j], pv.x);
-                  s[v][j + 1] = (f == 0) ? pv.y : __fadd_rn(s[v][j + 1], pv.y);
+                  const uint32_t wr = w32[((VZ - 1 - v) * HC + j) >> 1];
+                  w = rzs[i] ? wr : w;
                 }
+                const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                s[v][j] = (f == 0) ? pv.x : __fadd_rn(s[v][j], pv.x);
+                s[v][j + 1] = (f == 0) ? pv.y : __fadd_rn(s[v][j + 1], pv.y);
               }
             }
           }
         }
       }
+    }
 #pragma unroll
-      for (int v = 0; v < VZ; ++v)
+    for (int v = 0; v < VZ; ++v) {
+      if (CONTIG || vok[v]) {
 #pragma unroll
         for (int j = 0; j < HC; ++j) {
           float c = s[v][j];
@@ -405,16 +436,17 @@ __global__ void __launch_bounds__(256, (HC <= 2 ? 4 : (HC <= 4 ? 3 : 2))) accumu
           if (gauss) c = __fmul_rn(c, g[v]);
           r[v][j] = __fadd_rn(r[v][j], c);
         }
+      }
     }
-    if (any) {
+  }
+  if (any) {
 #pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        if (h0 + j < heads) {
-          if constexpr (VZ == 4)
-            *reinterpret_cast<float4*>(a0 + (size_t)(h0 + j) * hstride) = make_float4(r[0][j], r[1][j], r[2][j], r[3][j]);
-          else
-            *reinterpret_cast<float2*>(a0 + (size_t)(h0 + j) * hstride) = make_float2(r[0][j], r[1][j]);
-        }
+    for (int j = 0; j < HC; ++j) {
+      if (h0 + j < heads) {
+        if constexpr (VZ == 4)
+          *reinterpret_cast<float4*>(a0 + (size_t)(h0 + j) * hstride) = make_float4(r[0][j], r[1][j], r[2][j], r[3][j]);
+        else
+          *reinterpret_cast<float2*>(a0 + (size_t)(h0 + j) * hstride) = make_float2(r[0][j], r[1][j]);
       }
     }
   }
@@ -680,9 +712,12 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
     else if (p_stride == 8) hc = 8;
     else if (p_stride % 16 == 0) { hc = 16; vz = 2; }
     else if (p_stride % 8 == 0) hc = 8;
-    if (hc && (pZ % vz || Z % vz)) hc = 0;
-    for (int t = 0; t < n_tiles && hc; ++t)
-      if (starts_host[t * 3 + 2] % vz) hc = 0;
+    if (hc && Z % vz) hc = 0;                       // the accumulator rows must hold whole z groups
+    if (hc && hc == p_stride) {                     // contiguous loads: tile z starts and extents in whole groups
+      if (pZ % vz) hc = 0;
+      for (int t = 0; t < n_tiles && hc; ++t)
+        if (starts_host[t * 3 + 2] % vz) hc = 0;
+    }
     static int cluster_enabled = -1;
     if (cluster_enabled < 0) {
       const char* e = getenv("FNNU_ACC_CLUSTER");
@@ -712,6 +747,9 @@ extern "C" int fnnu_accumulate_tiles(const void* preds, int in_dtype, int p_stri
         tc.idx[tc.n] = t;
         ++tc.n;
       }
+      // the box is aligned to whole z groups of the ACCUMULATOR (tile starts may be odd)
+      lo[2] = lo[2] / vz * vz;
+      hi[2] = (hi[2] + vz - 1) / vz * vz;
       tc.ox = lo[0]; tc.oy = lo[1]; tc.oz = lo[2];
       tc.bx = hi[0] - lo[0]; tc.by = hi[1] - lo[1]; tc.bz = hi[2] - lo[2];
       FNNU_CHECK_ARG((size_t)8 * pvox * p_stride < ((size_t)1 << 32) && tc.bx <= 65535, "accumulate: tile too large for the 32-bit offsets");

@@ -71,7 +71,10 @@ def test_accumulate_fp16_emulation_bit_exact(vol, patch, heads):
                                                      ((33, 35, 41), (16, 24, 20), 3, 8), ((48, 32, 32), (32, 32, 32), 61, 64),
                                                      # cluster kernel variants: 4 / 8 / 16 heads per load, 2 or 4 z voxels
                                                      ((48, 40, 48), (32, 32, 32), 4, 4), ((40, 40, 40), (32, 24, 32), 7, 8),
-                                                     ((40, 48, 38), (32, 32, 32), 25, 32), ((36, 36, 44), (24, 24, 24), 3, 4)])
+                                                     ((40, 48, 38), (32, 32, 32), 25, 32), ((36, 36, 44), (24, 24, 24), 3, 4),
+                                                     # odd tile starts along z (cfg 5's tiles start at 46, 139, 185 ...): voxel-by-voxel loads
+                                                     ((36, 40, 50), (24, 24, 32), 25, 32), ((30, 36, 50), (24, 24, 32), 61, 64),
+                                                     ((30, 36, 50), (24, 24, 32), 7, 8)])
 @pytest.mark.parametrize('chunk', [0, 4, 7])
 def test_accumulate_tta_fp32(vol, patch, heads, pstride, chunk):
     """fp16 predictions of 8 mirrored passes -> un-flip, mean, Gaussian weight, fp32 accumulate, normalise."""

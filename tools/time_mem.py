@@ -32,10 +32,10 @@ def timed(fn, reps=5):
     return float(np.median(ts))
 
 
-def run(name, patch, heads, ps, n_tiles, vol):
+def run(name, patch, heads, ps, n_tiles, vol, zstarts=None):
     P = int(np.prod(patch))
     step = patch[2] // 2
-    starts = np.array([[0, 0, i * step] for i in range(n_tiles)], dtype=np.int32)
+    starts = np.array([[0, 0, (zstarts[i] if zstarts else i * step)] for i in range(n_tiles)], dtype=np.int32)
     preds = (torch.randn((n_tiles * 8, *patch, ps), device=dev) * 2).half()
     g16 = torch.from_numpy(sw.compute_gaussian(patch, 1. / 8, 10, np.float16)).to(dev)
     acc = torch.zeros((heads, *vol), dtype=torch.float32, device=dev)
@@ -74,6 +74,7 @@ print({k: v for k, v in os.environ.items() if k.startswith('FNNU_')})
 run('cfg2 (2 heads, 128^3)', (128, 128, 128), 2, 2, 4, (128, 128, 320))
 run('cfg4 (4 heads, 128^3)', (128, 128, 128), 4, 4, 4, (128, 128, 320))
 run('cfg5 (61 heads, 160x96x96)', (160, 96, 96), 61, 64, 4, (160, 96, 240))
+run('cfg5, real tile starts 0 46 92 139', (160, 96, 96), 61, 64, 4, (160, 96, 236), zstarts=[0, 46, 92, 139])
 # gather
 vol = torch.randn((1, 400, 512, 512), device=dev)
 starts = sw.tile_starts((400, 512, 512), (128, 128, 128), 0.5)[:4]
