@@ -591,8 +591,9 @@ int launch_conv_specialised(const ConvArgs& a, cudaStream_t s) {
     return FNNU_OK;
   }
   if (small_cin_ok(a)) {
-    // Cin == 1 first layers run on the tensor cores (conv_first_umma.cu); FNNU_FIRST_LAYER_TC=0 selects the CUDA-core kernel
+    // Cin == 1 first layers run on the tensor cores (conv_first_zpair.cu, conv_first_umma.cu); FNNU_FIRST_LAYER_TC=0 selects the CUDA-core kernel
     static const bool first_tc = [] { const char* e = getenv("FNNU_FIRST_LAYER_TC"); return !(e && e[0] == '0'); }();
+    if (first_tc && first_zpair_supported(a)) return launch_conv_first_zpair(a, s);
     if (first_tc && first_umma_supported(a)) return launch_conv_first_umma(a, s);
     long long groups = (long long)a.out_d[0] * a.out_d[1] * ((a.out_d[2] + 3) / 4);
     dim3 grid((unsigned)((groups + 127) / 128), (unsigned)(a.cout_pad / 16), (unsigned)a.batch);

@@ -80,5 +80,9 @@ int launch_conv_zrows(const ConvArgs& a, cudaStream_t s);
 // FNNU_FIRST_LAYER_TC=0 restores the CUDA-core kernel)
 bool first_umma_supported(const ConvArgs& a);
 int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s);
+// conv_first_zpair.cu: the same layer with (plane, ky) as K, kx as a descriptor shift and two output planes per MMA
+// (Cout padded to 16 or 32; FNNU_FIRST_ZPAIR=0 falls back to conv_first_umma.cu)
+bool first_zpair_supported(const ConvArgs& a);
+int launch_conv_first_zpair(const ConvArgs& a, cudaStream_t s);
 
 }  // namespace fnnu

@@ -123,7 +123,7 @@ def test_student_128_he_init_forward_matches_oracle():
 
 
 @pytest.mark.parametrize('name', ['SMALL_PLAIN16', 'ANISO_PLAIN', 'SMALL_RESENC', 'ROWS_W128', 'ROWS_W96', 'ROWS_W64_C32',
-                                  'ZROWS_W96', 'ZROWS_W72_H9', 'ZROWS_ODD_D'])
+                                  'ZROWS_W96', 'ZROWS_W72_H9', 'ZROWS_ODD_D', 'TINY_ONNX'])
 def test_tcgen05_layers_match_direct_kernel(name):
     """Every activation buffer written with the tcgen05 implicit-GEMM back end against the CUDA-core direct
     kernel (same fp16 inputs, fp32 accumulation in both): differences are fp32 summation order + one fp16 ulp."""
