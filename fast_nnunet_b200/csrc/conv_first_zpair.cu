@@ -32,10 +32,15 @@ constexpr int kFzStages = 12;
 constexpr int kFzProw = 140;             // positions per 8-k group: 1 + 128 + 1, padded to 4 (mod 8)
 constexpr int kFzStageBytes = 2 * kFzProw * 16;
 constexpr int kFzStepBars = 16;
+#ifndef FNNU_FZ_AHEAD
+#define FNNU_FZ_AHEAD 4
+#endif
+constexpr int kFzAhead = FNNU_FZ_AHEAD;   // input rows in flight per plane and thread
 
 struct FzArgs {
   ConvArgs a;
   int n_units;     // batch * ceil(D / 2)
+  int units_per_cta;
 };
 
 // CP = 16: two CTAs per SM with 256 TMEM columns each.  CP = 32: an epilogue thread carries 64 fp32 InstanceNorm sums, so
@@ -55,11 +60,16 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
   uint64_t* step_bar = full_bar + kFzStages;                              // [kFzStepBars]
   uint64_t* tempty_bar = step_bar + kFzStepBars;                          // [8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 8);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);                 // [32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int D = a.in_d[0], H = a.in_d[1], W = a.in_d[2];
   const int n_zp = (D + 1) >> 1;
+  // consecutive z pairs per CTA: neighbouring pairs share two input planes (L2 hits a few microseconds apart) and a CTA
+  // changes sample - which flushes the InstanceNorm sums - at most a few times
+  const int u_begin = (int)blockIdx.x * p.units_per_cta;
+  const int u_end = u_begin + p.units_per_cta < p.n_units ? u_begin + p.units_per_cta : p.n_units;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFzStages; ++s) mbar_init(&full_bar[s], 4);      // one arrival per producer warp
@@ -76,6 +86,7 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
     if (k < NPL * 3 && kz >= 0 && kz < NKZ && co < a.cout) v = __ldg(a.w + (size_t)((kz * 3 + ky) * 3 + kx) * a.cout_pad + co);
     *reinterpret_cast<__half*>(b_s + ((kx * 2 + (k >> 3)) * N + n) * 16 + (k & 7) * 2) = __float2half_rn(v);
   }
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = (a.bias && (int)threadIdx.x < a.cout) ? __ldg(a.bias + threadIdx.x) : 0.f;
   // the ring starts as zeros: the producers never write the halo positions (x = -1, x >= W)
   for (int i = threadIdx.x; i < kFzStages * kFzStageBytes / 16; i += kFzThreads)
     reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
@@ -94,12 +105,13 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
     const int x = threadIdx.x;
     const bool col_ok = x < W;
     const uint32_t dst0 = smem_u32(ring) + (uint32_t)(x + 1) * 16u;
+    const uint32_t row_stride = (uint32_t)W * (uint32_t)a.src_cs;
     // IDENT: the source carries no pending transform (the gathered image) - the usual case
     auto produce = [&](auto ident_tag) {
       constexpr bool IDENT = decltype(ident_tag)::value;
       int t = 0, stage = 0, cur_b = -1;
       float sc = 1.f, sh = 0.f, sl = 1.f;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = u_begin; u < u_end; ++u) {
         const int b = u / n_zp, z0 = 2 * (u - b * n_zp);
         if (!IDENT && b != cur_b) {
           const ChanMeta m = a.src_meta[0];
@@ -108,35 +120,48 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
           cur_b = b;
         }
         const __half* vol = a.src + (size_t)b * D * H * W * a.src_cs + (size_t)x * a.src_cs;
-        auto in_image = [&](int pl, int yy) {
+        // 32-bit element offsets from the sample base; a plane outside the volume (or a column beyond W) never loads
+        uint32_t plane_off[NPL];
+        bool plane_ok[NPL];
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
           const int zz = z0 - PZ + pl;
-          return col_ok && zz >= 0 && zz < D && yy >= 0 && yy < H;
-        };
+          plane_ok[pl] = col_ok && zz >= 0 && zz < D;
+          plane_off[pl] = plane_ok[pl] ? (uint32_t)zz * (uint32_t)H * row_stride : 0u;
+        }
+        auto in_image = [&](int pl, int yy) { return plane_ok[pl] && yy < H; };      // yy >= 0 at every call
         auto load = [&](int pl, int yy) {      // raw value, 0 outside the image
           __half v = __float2half_rn(0.f);
-          if (in_image(pl, yy)) v = __ldg(vol + ((size_t)(z0 - PZ + pl) * H + yy) * W * a.src_cs);
+          if (in_image(pl, yy)) v = __ldg(vol + (plane_off[pl] + (uint32_t)yy * row_stride));
           return v;
         };
         auto xf = [&](__half raw, int pl, int yy) {   // the padding stays 0: it pads the TRANSFORMED tensor
           if (IDENT || !in_image(pl, yy)) return raw;
           return __float2half_rn(lrelu(fmaf(__half2float(raw), sc, sh), sl));
         };
-        // win[pl][r]: rows y-1, y, y+1 of input plane z0 - PZ + pl at column x; nxt[pl]: row y+2, raw, in flight
-        __half win[NPL][3], nxt[NPL];
+        // win[pl][r]: rows y-1, y, y+1 of input plane z0 - PZ + pl at column x; ahead[pl][i]: rows y+1 .. y+kFzAhead,
+        // raw, in flight (row r in slot (r - 1) % kFzAhead) - one row of look-ahead left every y-step waiting a full
+        // HBM latency (0.82 ms per 32 patches)
+        __half win[NPL][3], ahead[NPL][kFzAhead];
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl) {
           win[pl][0] = __float2half_rn(0.f);
           win[pl][1] = __float2half_rn(0.f);        // row -1 after the first shift
           win[pl][2] = xf(load(pl, 0), pl, 0);
-          nxt[pl] = load(pl, 1);
+#pragma unroll
+          for (int i = 0; i < kFzAhead; ++i) ahead[pl][i] = load(pl, i + 1);
         }
-        for (int y = 0; y < H; ++y, ++t) {
+        for (int yb = 0; yb < H; yb += kFzAhead) {
+#pragma unroll
+        for (int j = 0; j < kFzAhead; ++j) {
+          const int y = yb + j;
+          if (y >= H) break;
 #pragma unroll
           for (int pl = 0; pl < NPL; ++pl) {
             win[pl][0] = win[pl][1];
             win[pl][1] = win[pl][2];
-            win[pl][2] = xf(nxt[pl], pl, y + 1);
-            nxt[pl] = load(pl, y + 2);              // first read one y-step from now
+            win[pl][2] = xf(ahead[pl][j], pl, y + 1);
+            ahead[pl][j] = load(pl, y + 1 + kFzAhead);
           }
           if (t >= kFzStages) {
             const int tp = t - kFzStages;
@@ -163,6 +188,8 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive_warp(&full_bar[stage]);
           if (++stage == kFzStages) stage = 0;
+          ++t;
+        }
         }
       }
     };
@@ -174,7 +201,7 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
     const uint64_t b_desc0 = make_desc(smem_u32(b_s), N * 16, 128);
     int t = 0, stage = 0, slot = 0;
     uint32_t phase = 0, sphase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = u_begin; u < u_end; ++u) {
       for (int y = 0; y < H; ++y, ++t) {
         mbar_wait(&tempty_bar[slot], sphase ^ 1);
         mbar_wait(&full_bar[stage], phase);
@@ -226,7 +253,7 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
       }
     };
     int t = 0, slot = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = u_begin; u < u_end; ++u) {
       const int b = u / n_zp, z = 2 * (u - b * n_zp) + k;
       if (b != cur_b) {
         flush_stats(cur_b);
@@ -245,15 +272,15 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
             tc_fence_before();
             mbar_arrive_warp(&tempty_bar[slot]);
           }
+          if (has_bias) {      // a branch, not 32 predicated-off loads and adds per row
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + bias_s[g0 + j]);
+          }
           if (col_ok && plane_ok) {
             __half2 hv[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
-              if (has_bias) {
-                v0 += __ldg(a.bias + g0 + j);
-                v1 += __ldg(a.bias + g0 + j + 1);
-              }
+              const float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
               hv[j >> 1] = __floats2half2_rn(v0, v1);
               // sums of the ROUNDED values, as every other conv kernel keeps them
               const float2 r = __half22float2(hv[j >> 1]);
@@ -313,11 +340,12 @@ int launch_conv_first_zpair(const ConvArgs& a, cudaStream_t s) {
   p.n_units = a.batch * ((a.in_d[0] + 1) / 2);
   const int N = 2 * a.cout_pad;
   // padded so that no more CTAs are resident per SM than the 512 TMEM columns allow (2 x 256 or 1 x 512)
-  size_t smem = (size_t)kFzStages * kFzStageBytes + (size_t)3 * 2 * N * 16 + (kFzStages + kFzStepBars + 8) * 8 + 64;
+  size_t smem = (size_t)kFzStages * kFzStageBytes + (size_t)3 * 2 * N * 16 + (kFzStages + kFzStepBars + 8) * 8 + 8 + 32 * 4 + 64;
   const size_t smem_min = a.cout_pad == 16 ? 78 * 1024 : 116 * 1024;
   if (smem < smem_min) smem = smem_min;
   const int ctas = (a.cout_pad == 16 ? 2 : 1) * num_sms();
-  const int grid = p.n_units < ctas ? p.n_units : ctas;
+  p.units_per_cta = (p.n_units + ctas - 1) / ctas;
+  const int grid = (p.n_units + p.units_per_cta - 1) / p.units_per_cta;
 #define FNNU_FZ_CASE(CPV, NKZV)                                                                                               \
   if (a.cout_pad == CPV && a.k[0] == NKZV) {                                                                                  \
     FNNU_CUDA(cudaFuncSetAttribute(conv_first_zpair_kernel<CPV, NKZV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); \
