@@ -35,6 +35,7 @@ struct Op {
   ConvArgs conv;
   EltArgs elt;
   bool umma_ok;
+  bool tconv_ok;     // conv_tconv_umma.cu takes this transposed conv
 };
 
 }  // namespace fnnu
@@ -263,6 +264,7 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
     Op& op = e->ops[i];
     op.kind = o.op;
     op.umma_ok = false;
+    op.tconv_ok = false;
     const Buf& sb = e->bufs[o.src];
     const Buf& db = e->bufs[o.dst];
     if (o.op == FNNU_OP_CONV || o.op == FNNU_OP_TCONV) {
@@ -326,6 +328,7 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       }
       a.batch = 1;
       op.umma_ok = a.w_umma != nullptr && (a.use_rows || umma_supported(a));
+      op.tconv_ok = a.transposed && tconv_umma_supported(a);
     } else {
       EltArgs& a = op.elt;
       memset(&a, 0, sizeof(a));
@@ -428,7 +431,10 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
     if (prof) FNNU_CUDA(cudaEventRecord(e->ev0, s));
     if (op.kind == FNNU_OP_CONV || op.kind == FNNU_OP_TCONV) {
       op.conv.batch = batch;
-      if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
+      if (e->backend == 0 && op.tconv_ok) {
+        rc = launch_tconv_umma(op.conv, s);
+        ++umma;
+      } else if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
         rc = op.conv.use_rows == 2 ? launch_conv_zrows(op.conv, s)
              : op.conv.use_rows   ? launch_conv_rows(op.conv, s)
                                   : launch_conv_umma(op.conv, s);

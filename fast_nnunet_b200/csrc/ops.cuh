@@ -85,4 +85,9 @@ int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s);
 bool first_zpair_supported(const ConvArgs& a);
 int launch_conv_first_zpair(const ConvArgs& a, cudaStream_t s);
 
+// conv_tconv_umma.cu: transposed conv with kernel == stride as one GEMM per 128 input voxels (Cin 32 / 64 / 128,
+// taps * Cout_pad <= 512; FNNU_TCONV_UMMA=0 leaves the layer to the generic kernel)
+bool tconv_umma_supported(const ConvArgs& a);
+int launch_tconv_umma(const ConvArgs& a, cudaStream_t s);
+
 }  // namespace fnnu
