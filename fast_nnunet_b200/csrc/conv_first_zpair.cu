@@ -230,6 +230,8 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
     const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(k * CP);
     const bool col_ok = x < W;
     const bool has_bias = a.bias != nullptr;
+    const bool vec_ok = (a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0);
+    const long long partner_delta = (long long)a.dst_cs * 2 * ((lane & 1) ? -1 : 1);     // lanes 2i / 2i+1: columns x, x+1
     const size_t out_row = (size_t)W * a.dst_cs;
     float s1[CP], s2[CP];
 #pragma unroll
@@ -276,12 +278,13 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + bias_s[g0 + j]);
           }
-          if (col_ok && plane_ok) {
-            __half2 hv[8];
+          const bool ok = col_ok && plane_ok;
+          __half2 hv[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) hv[j >> 1] = __floats2half2_rn(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
+          if (ok) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
-              hv[j >> 1] = __floats2half2_rn(v0, v1);
               // sums of the ROUNDED values, as every other conv kernel keeps them
               const float2 r = __half22float2(hv[j >> 1]);
               s1[g0 + j] += r.x;
@@ -289,15 +292,15 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
               s1[g0 + j + 1] += r.y;
               s2[g0 + j + 1] = fmaf(r.y, r.y, s2[g0 + j + 1]);
             }
-            __half* q = out_px + g0;
-            if ((a.dst_cs % 8 == 0) && (((uintptr_t)a.dst) % 16 == 0) && g0 + 16 <= a.cout) {
-              reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
-              reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[4]);
-            } else {
+          }
+          __half* q = out_px + g0;
+          if (vec_ok && g0 + 16 <= a.cout) {
+            // whole 32-byte sectors per instruction (see stg32_paired)
+            stg32_paired(q, partner_delta, *reinterpret_cast<uint4*>(&hv[0]), *reinterpret_cast<uint4*>(&hv[4]), ok, lane);
+          } else if (ok) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (g0 + j < a.cout) q[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (g0 + j < a.cout) q[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
           }
         }
         if (++slot == SLOTS) slot = 0;

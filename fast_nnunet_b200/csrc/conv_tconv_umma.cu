@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTcThreads, GROUPS == 4 ? 2 : 1) conv_tconv_um
   uint64_t* tfull_bar = empty_bar + kTcMaxStages;                    // [4]
   uint64_t* tempty_bar = tfull_bar + 4;                              // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
-  int* col_off = reinterpret_cast<int*>(tmem_slot + 2);              // [n_total / 16] output offset of a 16-column group
+  int* col_off = reinterpret_cast<int*>(tmem_slot + 4);              // [n_total / 16] output offset of a 16-column group
   float* bias_s = reinterpret_cast<float*>(col_off + 32);            // [128]
 
   const int warp = threadIdx.x >> 5;
@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(kTcThreads, GROUPS == 4 ? 2 : 1) conv_tconv_um
     const int half_groups = c.nb / 32;                 // 16-column groups of a pass that this set handles
     const bool vec_ok = (a.cout % 16) == 0;
     const bool has_bias = a.bias != nullptr;
+    // lanes 2i / 2i+1 are neighbours in x (W is even: 128 divides the voxel count and tiles start at multiples of 128)
+    const bool paired = vec_ok && (W % 2) == 0;
+    const long long partner_delta = (long long)a.s[2] * a.dst_cs * 2 * ((lane & 1) ? -1 : 1);
     const long long out_sample = (long long)a.out_d[0] * Ho * Wo * a.dst_cs;
     int slot = 0;
     uint32_t sphase = 0;
@@ -289,14 +292,23 @@ __global__ void __launch_bounds__(kTcThreads, GROUPS == 4 ? 2 : 1) conv_tconv_um
           const int n0 = ps * c.nb + col;
           const int co0 = n0 % CP;
           if (has_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + co0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + bias_s[co0 + j]);
+            for (int j = 0; j < 4; ++j) {
+              const float4 bv = b4[j];
+              acc[4 * j + 0] = __float_as_uint(__uint_as_float(acc[4 * j + 0]) + bv.x);
+              acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + bv.y);
+              acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + bv.z);
+              acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + bv.w);
+            }
           }
           __half2 hv[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) hv[j >> 1] = __floats2half2_rn(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
           __half* q = out_v + col_off[n0 >> 4];
-          if (vec_ok) {
+          if (paired) {
+            stg32_paired(q, partner_delta, *reinterpret_cast<uint4*>(&hv[0]), *reinterpret_cast<uint4*>(&hv[4]), true, lane);
+          } else if (vec_ok) {
             reinterpret_cast<uint4*>(q)[0] = *reinterpret_cast<uint4*>(&hv[0]);
             reinterpret_cast<uint4*>(q)[1] = *reinterpret_cast<uint4*>(&hv[4]);
           } else {

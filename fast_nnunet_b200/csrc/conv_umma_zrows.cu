@@ -536,6 +536,9 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
     const bool col_ok = x < c.W;
     const bool has_bias = a.bias != nullptr;
     const size_t out_row_stride = (size_t)c.W * a.dst_cs;
+#ifdef FNNU_ZROWS_PAIRED_STORE
+    const long long partner_delta = (long long)a.dst_cs * 2 * ((lane & 1) ? -1 : 1);     // lanes 2i / 2i+1: columns x, x+1
+#endif
     float s1[16], s2[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
@@ -596,6 +599,36 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
           // the tile of step t is fully consumed (its ky = 1, 2 groups were used by the two previous rows)
           tc_fence_before();
           mbar_arrive_warp(&tempty_bar[slot_a]);
+#ifdef FNNU_ZROWS_PAIRED_STORE
+          {
+            __half2 hv[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float v0 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+              float v1 = (__uint_as_float(r0[j + 1]) + __uint_as_float(r1[j + 1])) + __uint_as_float(r2[j + 1]);
+              if (has_bias) {       // only a convolution WITHOUT a following InstanceNorm keeps its bias (program.py)
+                const float2 bj = *reinterpret_cast<const float2*>(bias_s + c0 + j);
+                v0 += bj.x;
+                v1 += bj.y;
+              }
+              if (col_ok) {
+                s1[j] += v0;
+                s2[j] = fmaf(v0, v0, s2[j]);
+                s1[j + 1] += v1;
+                s2[j + 1] = fmaf(v1, v1, s2[j + 1]);
+              }
+              hv[j >> 1] = __floats2half2_rn(v0, v1);
+            }
+            if (vec_store) {
+              // whole 32-byte sectors per instruction (umma_ptx.cuh: stg32_paired)
+              stg32_paired(out_px, partner_delta, *reinterpret_cast<uint4*>(&hv[0]), *reinterpret_cast<uint4*>(&hv[4]), col_ok, lane);
+            } else if (col_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < a.cout) out_px[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
+            }
+          }
+#else
           if (col_ok) {
             __half2 hv[8];
 #pragma unroll
@@ -622,6 +655,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_umma_zrows_kernel(const __g
                 if (c0 + j < a.cout) out_px[j] = (j & 1) ? __high2half(hv[j >> 1]) : __low2half(hv[j >> 1]);
             }
           }
+#endif
         }
         ++t;
         slot_a = slot_b;

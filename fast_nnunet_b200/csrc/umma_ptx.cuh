@@ -130,4 +130,33 @@ __device__ __forceinline__ uint4 xform8_h2(const uint4 raw, const __half2* s2, c
   return o;
 }
 
+// 32 bytes per lane to addresses that differ between neighbouring lanes (NDHWC rows: one voxel per lane).  Two plain
+// 16-byte stores per lane write HALF a 32-byte sector per lane and instruction, and L1 forwards every partial sector to
+// L2 as a whole one (ncu on the transposed conv: l1tex2xbar write bytes = 2x the data, l1tex throughput 88 %).  Here
+// lanes 2i and 2i+1 swap halves so that each instruction writes whole sectors: first the even lane's voxel (even lane
+// the low half, odd lane the high half), then the odd lane's.  All 32 lanes must call; `partner_delta` is the byte
+// distance from a lane's own address to its partner's (+stride for even lanes, -stride for odd lanes); `ok` predicates
+// the lane's OWN voxel.
+__device__ __forceinline__ void stg32_paired(void* q_own, long long partner_delta, const uint4 lo, const uint4 hi, bool ok, int lane) {
+  const bool odd = lane & 1;
+  const uint4 send = odd ? lo : hi;
+  uint4 recv;
+  recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+  recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+  recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+  recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+  const bool partner_ok = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
+  char* own = reinterpret_cast<char*>(q_own);
+  char* partner = own + partner_delta;
+  // instruction 1: the even lane's voxel; instruction 2: the odd lane's voxel
+  char* a1 = odd ? partner + 16 : own;
+  char* a2 = odd ? own + 16 : partner;
+  const uint4 d1 = odd ? recv : lo;
+  const uint4 d2 = odd ? hi : recv;
+  const bool ok1 = odd ? partner_ok : ok;
+  const bool ok2 = odd ? ok : partner_ok;
+  if (ok1) *reinterpret_cast<uint4*>(a1) = d1;
+  if (ok2) *reinterpret_cast<uint4*>(a2) = d2;
+}
+
 }  // namespace fnnu
