@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.environ.get('FNNU_BUILD_OUT') or os.path.join(HERE, 'libfnnu.so')
 OBJ = os.path.join(HERE, 'csrc', '_build' + ('_alt' if os.environ.get('FNNU_BUILD_OUT') else ''))
 SOURCES = ['engine.cu', 'mem_kernels.cu', 'export_kernels.cu', 'preprocess_kernels.cu', 'conv_ref.cu', 'conv_umma.cu', 'conv_umma_rows.cu', 'conv_umma_zrows.cu',
-           'conv_first_umma.cu', 'conv_first_zpair.cu', 'conv_tconv_umma.cu']
+           'conv_first_umma.cu', 'conv_first_zpair.cu', 'conv_tconv_umma.cu', 'conv_s2_umma.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',

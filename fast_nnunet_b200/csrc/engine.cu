@@ -36,6 +36,7 @@ struct Op {
   EltArgs elt;
   bool umma_ok;
   bool tconv_ok;     // conv_tconv_umma.cu takes this transposed conv
+  bool s2_ok;        // conv_s2_umma.cu takes this stride-2 conv
 };
 
 }  // namespace fnnu
@@ -265,6 +266,7 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
     op.kind = o.op;
     op.umma_ok = false;
     op.tconv_ok = false;
+    op.s2_ok = false;
     const Buf& sb = e->bufs[o.src];
     const Buf& db = e->bufs[o.dst];
     if (o.op == FNNU_OP_CONV || o.op == FNNU_OP_TCONV) {
@@ -329,6 +331,7 @@ extern "C" int fnnu_engine_create(const fnnu_buffer_desc* bufs, int n_bufs, cons
       a.batch = 1;
       op.umma_ok = a.w_umma != nullptr && (a.use_rows || umma_supported(a));
       op.tconv_ok = a.transposed && tconv_umma_supported(a);
+      op.s2_ok = s2_umma_supported(a);
     } else {
       EltArgs& a = op.elt;
       memset(&a, 0, sizeof(a));
@@ -433,6 +436,9 @@ extern "C" int fnnu_engine_forward(fnnu_engine* e, int batch, void* stream) {
       op.conv.batch = batch;
       if (e->backend == 0 && op.tconv_ok) {
         rc = launch_tconv_umma(op.conv, s);
+        ++umma;
+      } else if (e->backend == 0 && op.s2_ok) {
+        rc = launch_conv_s2_umma(op.conv, s);
         ++umma;
       } else if (e->backend == 0 && op.umma_ok && !prefer_cuda_cores(op.conv)) {
         rc = op.conv.use_rows == 2 ? launch_conv_zrows(op.conv, s)

@@ -90,4 +90,9 @@ int launch_conv_first_zpair(const ConvArgs& a, cudaStream_t s);
 bool tconv_umma_supported(const ConvArgs& a);
 int launch_tconv_umma(const ConvArgs& a, cudaStream_t s);
 
+// conv_s2_umma.cu: stride-2 3x3x3 conv 16 -> <= 32 channels, row-streaming over the NDHWC row seen as position pairs
+// (FNNU_S2_UMMA=0 leaves the layer to the generic kernel)
+bool s2_umma_supported(const ConvArgs& a);
+int launch_conv_s2_umma(const ConvArgs& a, cudaStream_t s);
+
 }  // namespace fnnu
