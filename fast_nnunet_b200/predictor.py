@@ -403,9 +403,9 @@ class nnUNetPredictor(object):
         self.last_launches += launches + (E.mem_launches() - m0)
 
     @torch.inference_mode()
-    def profile_dominant_op(self, data: torch.Tensor, n_batches: int = 6):
+    def profile_dominant_op(self, data: torch.Tensor, n_batches: int = 6, op_name: str = None):
         """bench.py: device time (CUDA events on the launching stream, inside libfnnu) of the network operator
-        with the most FLOPs, over `n_batches` real tile batches of `data`."""
+        with the most FLOPs (or of the operator called `op_name`), over `n_batches` real tile batches of `data`."""
         patch = tuple(self.configuration_manager.patch_size)
         flips = self._flip_masks()
         nf = len(flips)
@@ -415,6 +415,11 @@ class nnUNetPredictor(object):
         prog = eng.program
         flops = [o.flops(prog.buffers[o.src][0], prog.buffers[o.dst][0]) for o in prog.ops]
         idx = int(np.argmax(flops))
+        if op_name is not None:
+            names = [o.name for o in prog.ops]
+            if op_name not in names:
+                raise KeyError(f'no operator named {op_name!r} in the program')
+            idx = names.index(op_name)
         eng.profile_op(idx)
         starts_dev = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.int32)).to(self.device)
         times = []

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Reads `ncu --set full` reports and writes the per-launch DRAM traffic of each captured kernel into
 profiles/r02_ncu_traffic.json (what bench.py's roofline.traffic quotes) plus a text summary.
-    python tools/ncu_traffic.py gpurun_out/x.ncu-rep:op_name:patches [more...]"""
+    python tools/ncu_traffic.py gpurun_out/x.ncu-rep:op_name:patches:cin:cout [more...]"""
 import csv
 import io
 import json
@@ -40,10 +40,10 @@ def read(rep):
 def main():
     caps, lines = [], []
     for arg in sys.argv[1:]:
-        rep, op, patches = (arg.split(':') + ['', '0'])[:3]
+        rep, op, patches, cin, cout = (arg.split(':') + ['', '0', '0', '0'])[:5]
         for d in read(rep):
             name = d['kernel'].split('(')[0].split('::')[-1].split('<')[0].strip()
-            caps.append({'kernel': name, 'kernel_full': d['kernel'][:120], 'op': op, 'patches_per_launch': int(patches),
+            caps.append({'kernel': name, 'kernel_full': d['kernel'][:120], 'op': op, 'patches_per_launch': int(patches), 'cin': int(cin), 'cout': int(cout),
                          'dram_bytes_read': d.get('dram__bytes_read.sum'), 'dram_bytes_write': d.get('dram__bytes_write.sum'),
                          'report': os.path.basename(rep)})
             lines.append(f"{os.path.basename(rep)}: {d['kernel'][:100]}")
