@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kFzThreads, CP == 16 ? 2 : 1) conv_first_zpair
           if (ok) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              // sums of the ROUNDED values, as every other conv kernel keeps them
+              // sums of the ROUNDED (stored) values, as the general and CUDA-core kernels keep them
               const float2 r = __half22float2(hv[j >> 1]);
               s1[g0 + j] += r.x;
               s2[g0 + j] = fmaf(r.x, r.x, s2[g0 + j]);
