@@ -436,6 +436,17 @@ def run_ours(args, wl):
                    'sec_per_volume': spv,
                    'sample': f'{CPU_BASELINE_TILES} of {n_total} tiles x 8 mirror passes ({dt:.1f} s of CPU work), '
                              f'extrapolated by tile count'}
+            # the reference caps its own CPU run at default_num_processes = 8 threads (predict_from_raw_data.py:479-480):
+            # the same sample, smaller, with that cap (SURVEY.md section 8d asks for both)
+            try:
+                capped = min(8, cores)
+                spv8, dt8, _ = cpu_reference_sample(wl, 2, capped)
+                cpu['reference_default_threads'] = {'cores': capped, 'value': nvox / spv8 / 1e6, 'unit': 'Mvoxel/s',
+                                                    'sec_per_volume': spv8,
+                                                    'sample': f'2 of {n_total} tiles x 8 mirror passes ({dt8:.1f} s of CPU work)'}
+                torch.set_num_threads(cores)
+            except Exception as ex:
+                cpu['reference_default_threads'] = {'error': repr(ex)}
         line = {
             'metric': 'sliding-window inference throughput', 'value': nvox / (ms * 1e-3) / 1e6, 'unit': 'Mvoxel/s',
             'sec_per_volume': ms * 1e-3, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

@@ -71,13 +71,14 @@ bool rows_supported(const ConvArgs& a);
 int launch_pack_weights_rows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_rows(const ConvArgs& a, cudaStream_t s);
 
-// z-pair row-streaming kernel (conv_umma_zrows.cu): Cout <= 16, Cin 16 | 32, 3x3x3, even depth; FNNU_ZROWS=0 disables it
+// row-streaming kernel, second generation (conv_umma_zrows.cu): 3x3x3 / 1x3x3, stride 1, Cin 16 | 32, Cout <= 32,
+// 64 <= W <= 128; two output planes per pass when Cout <= 16, 3x3x3 and the depth is even; FNNU_ZROWS=0 disables it
 bool zrows_supported(const ConvArgs& a);
 int launch_pack_weights_zrows(const float* w_dev, void* out, const ConvArgs& a, cudaStream_t s);
 int launch_conv_zrows(const ConvArgs& a, cudaStream_t s);
 
-// conv_first_umma.cu: Cin == 1 first layer with the taps as the K dimension of the MMA (on by default;
-// FNNU_FIRST_LAYER_TC=0 restores the CUDA-core kernel)
+// conv_first_umma.cu: Cin == 1 first layer with the 27 taps as the K dimension of the MMA (round 1; runs only when
+// conv_first_zpair.cu is switched off or does not take the shape; FNNU_FIRST_LAYER_TC=0 selects the CUDA-core kernel)
 bool first_umma_supported(const ConvArgs& a);
 int launch_conv_first_umma(const ConvArgs& a, cudaStream_t s);
 // conv_first_zpair.cu: the same layer with (plane, ky) as K, kx as a descriptor shift and two output planes per MMA
