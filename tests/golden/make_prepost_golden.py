@@ -17,6 +17,13 @@ by stubs.  What each golden section therefore pins:
   nonzero_mask           cropping.py create_nonzero_mask — reference code + scipy.ndimage.binary_fill_holes
   crop_to_nonzero        cropping.py crop_to_nonzero — with acvl_utils' get_bbox_from_mask / bounding_box_to_slice STUBBED
                          (restated from the published package); pins everything but those two helpers
+  preprocessor           default_preprocessor.py DefaultPreprocessor.run_case_npy (no segmentation) — the reference's flow
+                         (transpose, crop_to_nonzero, normalise BEFORE resampling, order-3 data resampling, recorded
+                         properties); leans on the skimage and bounding-box stubs above
+  export                 export_prediction.py convert_predicted_logits_to_segmentation_with_correct_shape — the reference's
+                         function end to end (resample with the plans' default resampling_fn_probabilities, argmax,
+                         un-crop, inverse transpose); leans on the skimage stub above and on a restated
+                         acvl_utils insert_crop_into_image
   label_manager          label_handling.py LabelManager — properties, convert_logits_to_segmentation (argmax and
                          region thresholds), reference code + torch
 
@@ -100,8 +107,33 @@ def install_stubs():
 
     _module('acvl_utils')
     _module('acvl_utils.cropping_and_padding')
+    def insert_crop_into_image(image, crop, bbox):
+        """restated from the published acvl_utils for a crop that lies inside the image (the export call)"""
+        sl = tuple([slice(None)] * (image.ndim - len(bbox)) + [slice(int(a), int(b)) for a, b in bbox])
+        image[sl] = crop if not isinstance(crop, torch.Tensor) else crop.numpy()
+        return image
+
     _module('acvl_utils.cropping_and_padding.bounding_boxes', get_bbox_from_mask=get_bbox_from_mask,
-            bounding_box_to_slice=bounding_box_to_slice, insert_crop_into_image=None)
+            bounding_box_to_slice=bounding_box_to_slice, insert_crop_into_image=insert_crop_into_image)
+    _module('batchgenerators.utilities.file_and_folder_operations', join=os.path.join, load_json=None, save_pickle=None)
+    _module('nnunetv2.training')
+    _module('nnunetv2.training.dataloading')
+    _module('nnunetv2.training.dataloading.nnunet_dataset', nnUNetDatasetBlosc2=object)
+    _module('nnunetv2.utilities.plans_handling')
+    _module('nnunetv2.utilities.plans_handling.plans_handler', PlansManager=object, ConfigurationManager=object)
+    _module('nnunetv2.utilities.label_handling')
+    _module('nnunetv2.inference')
+    from typing import List, Tuple, Union
+    _module('SimpleITK')
+    _module('batchgenerators.utilities.file_and_folder_operations', join=os.path.join, load_json=None, save_pickle=None,
+            isdir=os.path.isdir, isfile=os.path.isfile, List=List, Tuple=Tuple, Union=Union, os=os,
+            __all__=['join', 'load_json', 'save_pickle', 'isdir', 'isfile', 'List', 'Tuple', 'Union', 'os'])
+    _module('nnunetv2.paths', nnUNet_preprocessed=None, nnUNet_raw=None)
+    _module('nnunetv2.utilities.dataset_name_id_conversion', maybe_convert_to_dataset_name=None)
+    _module('nnunetv2.utilities.utils', get_filenames_of_train_images_and_targets=None)
+    _module('nnunetv2.preprocessing')
+    _module('nnunetv2.preprocessing.cropping')
+    _module('nnunetv2.preprocessing.resampling')
     return aniso
 
 
@@ -110,7 +142,15 @@ def main():
     res = _load(os.path.join(REF, 'preprocessing/resampling/default_resampling.py'), 'ref_resampling')
     norm = _load(os.path.join(REF, 'preprocessing/normalization/default_normalization_schemes.py'), 'ref_norm')
     crop = _load(os.path.join(REF, 'preprocessing/cropping/cropping.py'), 'ref_cropping')
-    lab = _load(os.path.join(REF, 'utilities/label_handling/label_handling.py'), 'ref_labels')
+    lab = _load(os.path.join(REF, 'utilities/label_handling/label_handling.py'), 'nnunetv2.utilities.label_handling.label_handling')
+    sys.modules['nnunetv2.utilities.label_handling.label_handling'] = lab
+    exp = _load(os.path.join(REF, 'inference/export_prediction.py'), 'ref_export')
+    sys.modules['nnunetv2.preprocessing.cropping.cropping'] = crop
+    sys.modules['nnunetv2.preprocessing.resampling.default_resampling'] = res
+    sys.modules['nnunetv2'].__path__ = ['/nonexistent']
+    sys.modules['nnunetv2.utilities.find_class_by_name'].recursive_find_python_class = \
+        lambda folder, class_name, current_module: getattr(norm, class_name, None)
+    prep = _load(os.path.join(REF, 'preprocessing/preprocessors/default_preprocessor.py'), 'ref_preprocessor')
 
     arrays, table = {}, {'aniso_threshold': aniso}
 
@@ -210,6 +250,95 @@ def main():
             'foreground_regions': None if not lm.has_regions else [list(r) if isinstance(r, (tuple, list)) else int(r) for r in lm.foreground_regions],
             'num_segmentation_heads': int(heads), 'seg_dtype': str(np.asarray(seg_out).dtype)}
     table['label_manager'] = lm_table
+
+    # ---- export: logits -> label map in the original geometry ---------------------------------------------------------
+    from functools import partial
+
+    class _PM:
+        def __init__(self, tf):
+            self.transpose_forward = list(tf)
+            self.transpose_backward = [int(i) for i in np.argsort(tf)]
+
+    class _CM:
+        def __init__(self, spacing):
+            self.spacing = list(spacing)
+            # the plans' default: "resampling_fn_probabilities": "resample_data_or_seg_to_shape",
+            # kwargs {"is_seg": false, "order": 1, "order_z": 0, "force_separate_z": null}
+            self.resampling_fn_probabilities = partial(res.resample_data_or_seg_to_shape, is_seg=False, order=1, order_z=0,
+                                                       force_separate_z=None)
+
+    export_cases = [
+        # name, logits shape, plans spacing, transpose_forward, original spacing (file order), shape before cropping
+        # (transposed), bbox, label dict
+        ('iso', (3, 10, 12, 9), (1.5, 1.5, 1.5), (0, 1, 2), (1.0, 1.0, 1.0), (19, 20, 16), [[2, 17], [1, 19], [0, 14]],
+         {'background': 0, 'a': 1, 'b': 2}),
+        ('sepz_transposed', (2, 6, 14, 12), (3.0, 0.8, 0.8), (2, 0, 1), (0.6, 0.6, 4.5), (11, 24, 20), [[1, 10], [2, 23], [0, 18]],
+         {'background': 0, 'a': 1}),
+        ('same_shape', (4, 7, 8, 9), (1.0, 1.0, 1.0), (1, 2, 0), (1.0, 1.0, 1.0), (9, 8, 12), [[1, 8], [0, 8], [2, 11]],
+         {'background': 0, 'a': 1, 'b': 2, 'c': 3}),
+    ]
+    exp_meta = []
+    for name, lshape, pspacing, tf, ospacing, before, bbox, ld in export_cases:
+        logits = (rng.standard_normal(lshape) * 2).astype(np.float16)
+        mid = [b - a for a, b in bbox]
+        props = {'spacing': list(ospacing), 'shape_after_cropping_and_before_resampling': mid,
+                 'shape_before_cropping': list(before), 'bbox_used_for_cropping': bbox}
+        lm = lab.LabelManager(ld, None)
+        pm = _PM(tf)
+        seg_out = exp.convert_predicted_logits_to_segmentation_with_correct_shape(logits.copy(), pm, _CM(pspacing), lm, props,
+                                                                                  return_probabilities=False)
+        arrays[f'exp_{name}_logits'] = logits
+        arrays[f'exp_{name}_seg'] = np.asarray(seg_out)
+        exp_meta.append({'name': name, 'plans_spacing': list(pspacing), 'transpose_forward': list(tf),
+                         'transpose_backward': pm.transpose_backward, 'properties': props,
+                         'num_foreground': len(lm.foreground_labels), 'seg_dtype': str(np.asarray(seg_out).dtype),
+                         'seg_shape': list(np.asarray(seg_out).shape)})
+    table['export'] = exp_meta
+
+    # ---- DefaultPreprocessor.run_case_npy ------------------------------------------------------------------------------
+    class _PPM:
+        def __init__(self, tf, props_per_channel):
+            self.transpose_forward = list(tf)
+            self.foreground_intensity_properties_per_channel = props_per_channel
+
+    class _PCM:
+        def __init__(self, spacing, schemes, use_mask):
+            self.spacing = list(spacing)
+            self.normalization_schemes = list(schemes)
+            self.use_mask_for_norm = list(use_mask)
+            # plans defaults: resampling_fn_data = resample_data_or_seg_to_shape(is_seg=False, order=3, order_z=0,
+            # force_separate_z=None); the segmentation branch is not part of the inference path
+            self.resampling_fn_data = partial(res.resample_data_or_seg_to_shape, is_seg=False, order=3, order_z=0,
+                                              force_separate_z=None)
+            self.resampling_fn_seg = lambda seg, new_shape, *a, **k: np.zeros((seg.shape[0], *new_shape), dtype=seg.dtype)
+
+    pre_cases = [
+        # name, raw shape (c, file order), spacing (file order), transpose_forward, target spacing, schemes, use_mask
+        ('ct_iso', (1, 14, 16, 15), (1.0, 1.0, 1.0), (0, 1, 2), (1.4, 1.4, 1.4), ['CTNormalization'], [False]),
+        ('mri_aniso_transposed', (2, 12, 13, 6), (0.8, 0.8, 3.5), (2, 0, 1), (3.5, 1.1, 1.1), ['ZScoreNormalization', 'ZScoreNormalization'], [True, True]),
+        ('no_resampling', (1, 9, 10, 11), (1.0, 1.0, 1.0), (0, 1, 2), (1.0, 1.0, 1.0), ['ZScoreNormalization'], [False]),
+    ]
+    pre_meta = []
+    ct_props = {'0': {'mean': 0.4, 'std': 1.3, 'percentile_00_5': -1.5, 'percentile_99_5': 2.5},
+                '1': {'mean': 0.0, 'std': 1.0, 'percentile_00_5': -2.0, 'percentile_99_5': 2.0}}
+    for name, shp, spacing, tf, target, schemes, use_mask in pre_cases:
+        raw = rng.standard_normal(shp).astype(np.float32) + 0.5
+        raw[:, :2] = 0                          # a zero border on the first file axis: cropped away
+        raw[:, -1] = 0
+        raw[:, :, :, :1] = 0
+        raw[:, 4:7, 5:8, 2:4] = 0               # enclosed zeros: stay inside the mask (fill-holes)
+        props_in = {'spacing': list(spacing)}
+        data, seg, props = prep.DefaultPreprocessor(verbose=False).run_case_npy(
+            raw.copy(), None, dict(props_in), _PPM(tf, ct_props), _PCM(target, schemes, use_mask), {})
+        arrays[f'pre_{name}_raw'] = raw
+        arrays[f'pre_{name}_data'] = np.asarray(data)
+        pre_meta.append({'name': name, 'spacing': list(spacing), 'transpose_forward': list(tf), 'target_spacing': list(target),
+                         'schemes': schemes, 'use_mask': use_mask, 'props_per_channel': ct_props,
+                         'shape_before_cropping': [int(v) for v in props['shape_before_cropping']],
+                         'bbox_used_for_cropping': [[int(a), int(b)] for a, b in props['bbox_used_for_cropping']],
+                         'shape_after_cropping_and_before_resampling': [int(v) for v in props['shape_after_cropping_and_before_resampling']],
+                         'data_dtype': str(np.asarray(data).dtype), 'data_shape': list(np.asarray(data).shape)})
+    table['preprocessor'] = pre_meta
 
     np.savez_compressed(os.path.join(HERE, 'prepost_golden.npz'), **arrays)
     with open(os.path.join(HERE, 'prepost_golden.json'), 'w') as f:

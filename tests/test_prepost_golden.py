@@ -101,3 +101,31 @@ def test_label_manager_equals_reference(name):
     seg = lm.convert_logits_to_segmentation(logits)
     seg = seg.numpy() if isinstance(seg, torch.Tensor) else np.asarray(seg)
     np.testing.assert_array_equal(seg.astype(np.int64), G[f'lm_{name}_seg'].astype(np.int64))
+
+
+@pytest.mark.parametrize('case', T['export'], ids=lambda c: c['name'])
+def test_oracle_export_equals_executed_reference(case):
+    """export_prediction.convert_predicted_logits_to_segmentation_with_correct_shape, run from the reference's own file
+    (plans' default order-1 probability resampling, LabelManager argmax, un-crop, inverse transpose)."""
+    logits, want = G[f"exp_{case['name']}_logits"], G[f"exp_{case['name']}_seg"]
+    assert str(want.dtype) == case['seg_dtype'] and list(want.shape) == case['seg_shape']
+    got = O_export.convert_predicted_logits_to_segmentation_with_correct_shape(
+        logits.copy(), case['plans_spacing'], case['transpose_forward'], case['transpose_backward'], case['properties'],
+        num_foreground=case['num_foreground'])
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize('case', T['preprocessor'], ids=lambda c: c['name'])
+def test_oracle_preprocessor_equals_executed_reference(case):
+    """DefaultPreprocessor.run_case_npy, run from the reference's own file: transpose, crop to the filled non-zero mask,
+    normalise before resampling, order-3 resampling, and the properties the export needs later."""
+    raw, want = G[f"pre_{case['name']}_raw"], G[f"pre_{case['name']}_data"]
+    assert str(want.dtype) == case['data_dtype'] and list(want.shape) == case['data_shape']
+    data, props = O_pre.run_case_npy(raw.copy(), {'spacing': case['spacing']}, case['transpose_forward'],
+                                     case['target_spacing'], case['schemes'], case['use_mask'], case['props_per_channel'])
+    assert [int(v) for v in props['shape_before_cropping']] == case['shape_before_cropping']
+    assert [[int(a), int(b)] for a, b in props['bbox_used_for_cropping']] == case['bbox_used_for_cropping']
+    assert [int(v) for v in props['shape_after_cropping_and_before_resampling']] == case['shape_after_cropping_and_before_resampling']
+    assert data.dtype == want.dtype and data.shape == want.shape
+    np.testing.assert_array_equal(data, want)
