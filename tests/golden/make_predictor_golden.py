@@ -15,6 +15,12 @@ to the reference's executed code; the `padded` case additionally depends on the 
 The network is the oracle's torch module (oracle/networks.py) with seeded weights — the reference treats the network
 as an opaque nn.Module, so this pins the LOOP (rows a2, a5, a6, a7, a10 of SURVEY.md section 8), not the network.
 
+The `model_folder` case goes through the reference's initialize_from_trained_model_folder on a folder written by
+fast_nnunet_b200.model_folder.write_model_folder (the fixture every GPU predictor test loads) with the reference's REAL
+plans_handler.py and label_handling.py: it shows that the reference reads that folder, records what it read, and pins
+the two-fold ensemble through the file-based entry.  The trainer class it looks up is a stand-in whose
+build_network_architecture returns the oracle network.
+
 Writes tests/golden/predictor_golden.npz + .json (the inputs are regenerated from seeds by the test).
 """
 import importlib.util
@@ -96,7 +102,7 @@ def install_stubs():
     _module('batchgenerators.utilities.file_and_folder_operations', load_json=nothing, join=os.path.join,
             isfile=os.path.isfile, maybe_mkdir_p=nothing, isdir=os.path.isdir, subdirs=nothing, save_json=nothing)
     pkg = _module('nnunetv2')
-    pkg.__path__ = []
+    pkg.__path__ = ['/nonexistent']
     _module('nnunetv2.configuration', default_num_processes=8)
     _module('nnunetv2.inference')
     _module('nnunetv2.inference.data_iterators', PreprocessAdapterFromNpy=object, preprocessing_iterator_fromfiles=nothing,
@@ -109,10 +115,43 @@ def install_stubs():
     _module('nnunetv2.utilities.find_class_by_name', recursive_find_python_class=nothing)
     _load(os.path.join(REF, 'utilities/helpers.py'), 'nnunetv2.utilities.helpers')
     _module('nnunetv2.utilities.json_export', recursive_fix_for_json_export=nothing)
+    # the REAL label handling and plans handling (their own absent imports stubbed)
+    import json as _json
+
+    def load_json(path):
+        with open(path) as f:
+            return _json.load(f)
+
+    sys.modules['batchgenerators.utilities.file_and_folder_operations'].load_json = load_json
+    _module('acvl_utils.cropping_and_padding.bounding_boxes', bounding_box_to_slice=nothing, insert_crop_into_image=nothing)
+    _module('nnunetv2.preprocessing')
+    _module('nnunetv2.preprocessing.resampling')
+    _module('nnunetv2.preprocessing.resampling.utils', recursive_find_resampling_fn_by_name=lambda name: (lambda *a, **k: None))
+    _module('nnunetv2.imageio')
+    _module('nnunetv2.imageio.reader_writer_registry', recursive_find_reader_writer_by_name=nothing)
+    _module('dynamic_network_architectures')
+    _module('dynamic_network_architectures.building_blocks')
+    _module('dynamic_network_architectures.building_blocks.helper', convert_dim_to_conv_op=lambda dim: torch.nn.Conv3d,
+            get_matching_instancenorm=lambda conv_op=None, dimension=None: torch.nn.InstanceNorm3d)
     _module('nnunetv2.utilities.label_handling')
-    _module('nnunetv2.utilities.label_handling.label_handling', determine_num_input_channels=nothing)
+    lab = _load(os.path.join(REF, 'utilities/label_handling/label_handling.py'), 'nnunetv2.utilities.label_handling.label_handling')
     _module('nnunetv2.utilities.plans_handling')
-    _module('nnunetv2.utilities.plans_handling.plans_handler', PlansManager=object, ConfigurationManager=object)
+    _load(os.path.join(REF, 'utilities/plans_handling/plans_handler.py'), 'nnunetv2.utilities.plans_handling.plans_handler')
+
+    class StandInTrainer:
+        @staticmethod
+        def build_network_architecture(architecture_class_name, arch_init_kwargs, arch_init_kwargs_req_import,
+                                       num_input_channels, num_output_channels, enable_deep_supervision=True):
+            from oracle import networks as N
+            return N.build_from_arch(architecture_class_name, arch_init_kwargs, num_input_channels, num_output_channels,
+                                     allow_init=False)
+
+    def find_class(folder, class_name, current_module):
+        return {'LabelManager': lab.LabelManager, 'nnUNetTrainer': StandInTrainer}.get(class_name)
+
+    sys.modules['nnunetv2.utilities.find_class_by_name'].recursive_find_python_class = find_class
+    lab.recursive_find_python_class = find_class
+    sys.modules['nnunetv2.utilities.plans_handling.plans_handler'].recursive_find_python_class = find_class
     _module('nnunetv2.utilities.utils', create_lists_from_splitted_dataset_folder=nothing)
 
 
@@ -167,6 +206,29 @@ def main():
         m['first_slicers'] = [[[s.start, s.stop] for s in sl[1:]] for sl in slicers[:4]]
         meta['cases'].append(m)
         print(case['name'], tuple(out.shape), 'tiles', len(slicers), 'range', float(out.float().min()), float(out.float().max()))
+    # ---- file-based entry: initialize_from_trained_model_folder on a folder written by write_model_folder ----------
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        folder = os.path.join(tmp, 'nnUNetTrainer__nnUNetPlans__3d_fullres')
+        for f in range(2):
+            sd = M.synthesize_state_dict(spec['cls'], spec['kw'], spec['in_ch'], spec['heads'], seed=777 + f, randomize_affine=True)
+            M.write_model_folder(folder, spec['cls'], spec['kw'], spec['patch'], sd, spec['in_ch'], spec['heads'], fold=f,
+                                 mirror_axes=(0, 1, 2))
+        p = ref.nnUNetPredictor(tile_step_size=0.5, use_gaussian=True, use_mirroring=True, perform_everything_on_device=False,
+                                device=torch.device('cpu'), verbose=False, verbose_preprocessing=False, allow_tqdm=False)
+        p.initialize_from_trained_model_folder(folder, use_folds=(0, 1), checkpoint_name='checkpoint_final.pth')
+        x = nets.ct_like_volume((20, 24, 16), spec['in_ch'], seed=12)
+        out = p.predict_logits_from_preprocessed_data(x)
+        arrays['model_folder'] = out.numpy()
+        meta['model_folder'] = {
+            'volume': [spec['in_ch'], 20, 24, 16], 'folds': [0, 1], 'seeds': [777, 778],
+            'trainer_name': p.trainer_name, 'allowed_mirroring_axes': list(p.allowed_mirroring_axes),
+            'patch_size': list(p.configuration_manager.patch_size), 'n_parameter_sets': len(p.list_of_parameters),
+            'num_segmentation_heads': int(p.label_manager.num_segmentation_heads),
+            'all_labels': [int(i) for i in p.label_manager.all_labels],
+            'network_arch_class_name': p.configuration_manager.network_arch_class_name}
+        print('model_folder', tuple(out.shape), meta['model_folder']['trainer_name'], meta['model_folder']['patch_size'])
+
     np.savez_compressed(os.path.join(HERE, 'predictor_golden.npz'), **arrays)
     with open(os.path.join(HERE, 'predictor_golden.json'), 'w') as f:
         json.dump(meta, f, indent=1)
