@@ -36,12 +36,19 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+LAST_ACTION = ''      # what the last build() call did: 'compiled N sources in T s' or 'up to date (digest ...)'
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LAST_ACTION
+    import time
     stamp = os.path.join(OBJ, 'stamp')
     dig = _digest()
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+        LAST_ACTION = f'up to date (source digest {dig[:12]}), nothing compiled'
         return OUT
     os.makedirs(OBJ, exist_ok=True)
+    t0 = time.time()
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace('.cu', '.o'))
@@ -63,6 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
     with open(stamp, 'w') as f:
         f.write(dig)
+    LAST_ACTION = f'compiled {len(SOURCES)} sources for sm_100a in {time.time() - t0:.0f} s (source digest {dig[:12]})'
     return OUT
 
 
