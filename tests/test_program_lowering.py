@@ -40,3 +40,22 @@ def test_student_checkpoint_from_teacher_plans_lowers_and_matches():
     with torch.no_grad():
         err = (run_program(prog, x) - net(x)).abs().max().item()
     assert err <= 2e-4
+
+
+@pytest.mark.parametrize('name,patch', [('STUDENT', (64, 64, 64)), ('TEACHER', (64, 64, 64)), ('RESENC_M_STUDENT', (64, 64, 64)),
+                                        ('BONE_TURBO', (32, 32, 32))])
+def test_baseline_architectures_lower_correctly(name, patch):
+    """The BASELINE.json architectures (all stages, block counts, anisotropic kernels / strides, 61 heads) at a patch the
+    CPU finishes in seconds: the lowering does not depend on the patch size beyond the buffer extents."""
+    spec = dict(getattr(nets, name))
+    spec['patch'] = patch
+    sd, net = nets.make(spec)
+    prog = build_program(spec['cls'], sd, spec['kw'], spec['in_ch'], spec['heads'], patch)
+    x = torch.randn((1, spec['in_ch'], *patch), generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = net(x)
+        got = run_program(prog, x)
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    print(f'{name}: {len(prog.ops)} ops, max|d| {err:.2e} (logit range {scale:.2f})')
+    assert got.shape == want.shape and err <= 5e-4 * max(1.0, scale)
