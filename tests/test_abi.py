@@ -60,3 +60,26 @@ def test_invalid_arguments_return_error_codes(lib_path):
     assert rc == -1
     with pytest.raises(_lib.FnnuError):
         _lib.check(rc)
+
+
+def test_c_host_compiles_links_and_runs(lib_path, tmp_path):
+    """include/fnnu.h is a C header (not only C++): a C99 host built with -Wall -Wextra -Werror links every declared entry
+    point and runs the calls that need no GPU (tests/c/abi_host.c) — no Python, no torch on that side of the boundary."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    src = os.path.join(ROOT, 'tests', 'c', 'abi_host.c')
+    taken = set(re.findall(r'\(void\*\)(fnnu_[a-z0-9_]+)', open(src).read()))
+    assert taken == set(_declared()), sorted(set(_declared()) ^ taken)
+    exe = str(tmp_path / 'abi_host')
+    libdir = os.path.dirname(lib_path)
+    cuda_lib = '/usr/local/cuda/lib64'
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-I', os.path.join(ROOT, 'include'), src,
+                        '-L', libdir, '-lfnnu', f'-Wl,-rpath,{libdir}', f'-Wl,-rpath-link,{cuda_lib}', '-o', exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ)
+    env['LD_LIBRARY_PATH'] = cuda_lib + ':' + env.get('LD_LIBRARY_PATH', '')
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and 'entry points linked' in r.stdout, r.stdout + r.stderr
